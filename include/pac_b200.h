@@ -1,0 +1,178 @@
+/*
+ * pac_b200.h -- C ABI of the B200-native engine for the WAK/"PAC" perceptual audio codec hot path.
+ *
+ * The reference (wisamreid/Perceptual-Audio-Codec) is pure Python and has no FFI; its boundary is the
+ * Python call surface PACFile.WriteDataBlock/ReadDataBlock -> codec.Encode/Decode.
+ * This header is what the Python shim modules in perceptual-audio-codec_b200/ (pacfile.py, codec.py,
+ * psychoac.py, mdct.py, window.py, quantize.py, bitalloc.py) bind through ctypes.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference/codec/).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a HOST pointer unless the comment says "host or device"
+ *     (those are resolved with cudaPointerGetAttributes);
+ *   - return value: 0 = ok, <0 = error (PAC_E_*); pac_last_error(ctx) gives the text;
+ *   - one context per GPU and host thread; contexts share nothing;
+ *   - there is NO CPU fallback: every function below launches sm_100a kernels or fails.
+ */
+#ifndef PAC_B200_H
+#define PAC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAC_OK 0
+#define PAC_E_ARG      (-1)   /* bad argument / unsupported parameter combination */
+#define PAC_E_CUDA     (-2)   /* CUDA runtime error (text in pac_last_error) */
+#define PAC_E_OVERFLOW (-3)   /* an output buffer was too small (no bytes were written past it) */
+#define PAC_E_FORMAT   (-4)   /* malformed .pac input */
+#define PAC_E_NODEVICE (-5)   /* no usable CUDA device */
+
+#define PAC_PRECISION_FP64 0  /* verification mode: bit-exact .pac bytes vs the reference */
+#define PAC_PRECISION_FP32 1  /* fast mode */
+
+#define PAC_NTABLES 10
+#define PAC_MAX_BANDS 32
+
+typedef struct PacCtx PacCtx;
+
+/* CodingParams attributes set at pacfile.py:452-457 (+ sampleRate/nChannels from pcmfile.py:44-60) */
+typedef struct {
+    int32_t sampleRate;
+    int32_t nChannels;            /* must be 2 (codec.py:46-47, psychoac.py:477) */
+    int32_t nMDCTLines;           /* 1024 (also 512/256 for the L2 entry points) */
+    int32_t nScaleBits;           /* 4 */
+    int32_t nMantSizeBits;        /* 4 */
+    int32_t nTableIDBits;         /* 4 */
+    double  targetBitsPerSample;  /* 2.27 */
+} PacParams;
+
+/* huffmanTables.pickle flattened by the host shim (Huffman.py:138-153, 256-262): for table ID t+1,
+ * magnitude v < nkeys[t] has code value code[off[t]+v] of len[off[t]+v] bits; len 0 = key absent
+ * (escape, Huffman.py:292-298).  esc_* = encodingTable[-1]. */
+typedef struct {
+    int32_t nkeys[PAC_NTABLES];
+    int32_t off[PAC_NTABLES];
+    const uint32_t *code;
+    const uint8_t *len;
+    uint32_t esc_code[PAC_NTABLES];
+    int32_t esc_len[PAC_NTABLES];
+} PacHuffTables;
+
+/* Optional per-block taps of pac_encode_batch (parity tests; any pointer may be NULL).
+ * B = max over streams of pac_num_blocks(nSamples[s]); arrays are [S][B]-major.
+ * Floating taps are always double on the host side (fp32 mode widens). */
+typedef struct {
+    int32_t *lrms;        /* [S][B]           bit b = LRMS[b]                      codec.py:96-102 */
+    int32_t *oscale;      /* [S][B][2]        overallScaleFactor                   codec.py:245 */
+    double  *smr;         /* [S][B][2][nBands]                                     psychoac.py:662-682 */
+    double  *lines;       /* [S][B][2][nMDCTLines] LRMS-selected, scaled lines     psychoac.py:663-680 */
+    int32_t *ba;          /* [S][B][2][nBands] bitAlloc                            codec.py:258 */
+    int32_t *sf;          /* [S][B][2][nBands] scaleFactor                         codec.py:274 */
+    int32_t *tableID;     /* [S][B][2]                                             Huffman.py:309 */
+    int32_t *nbytes;      /* [S][B][2]        chunk payload bytes                  pacfile.py:291-317 */
+    int64_t *extraBits;   /* [S][B]           cp.extraBits after the block         codec.py:229,260 */
+    int64_t *bitDeposit;  /* [S][B]           huffman.bitDeposit after the block   codec.py:120 */
+} PacTrace;
+
+/* ------------------------------------------------------------------ context */
+/* replaces: Huffman() + the CodingParams set-up in pacfile.py:394,446-471 */
+int  pac_ctx_create(int device, int precision, const PacParams *params, const PacHuffTables *tables, PacCtx **out);
+void pac_ctx_destroy(PacCtx *ctx);
+const char *pac_last_error(PacCtx *ctx);          /* ctx may be NULL: error of the last failed pac_ctx_create */
+const char *pac_version(void);
+/* psychoac.py:124-156 + ScaleFactorBands :193-213 */
+int  pac_band_layout(PacCtx *ctx, int32_t *nLines /*[PAC_MAX_BANDS]*/, int32_t *nBands);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t pac_launch_count(PacCtx *ctx);
+
+/* ------------------------------------------------------------------ whole streams (the hot path) */
+/* ceil(n/nMDCTLines)+1: pcmfile.py:66-82 + the flush block of pacfile.py:355-365 */
+int64_t pac_num_blocks(PacCtx *ctx, int64_t nSamples);
+/* safe per-stream output capacity for pac_encode_batch */
+int64_t pac_encode_bound(PacCtx *ctx, int64_t nSamples);
+
+/* replaces the Encode pass of pacfile.py:430-499 for S independent streams:
+ *   PCMFile.ReadDataBlock (pcmfile.py:66-100) -> PACFile.WriteDataBlock (pacfile.py:273-353) -> codec.Encode
+ *   (codec.py:83-129) -> EncodeDualChannel (:212-281) -> getStereoMaskThreshold (psychoac.py:506-682) -> BitAlloc
+ *   (bitalloc.py:129-184) -> ScaleFactor/vMantissa (quantize.py:148-177,315-342) -> Huffman.encodeData
+ *   (Huffman.py:274-309) -> PackedBits.WriteBits (bitpack.py:36-101), plus WriteFileHeader (pacfile.py:231-271)
+ *   and the flush block of Close (pacfile.py:355-366).
+ * pcm: interleaved int16 [S][strideSamples][2], host or device.  nSamples[s] <= strideSamples (host).
+ * out: [S][cap] bytes, host or device; outBytes[s] (host) = bytes of stream s's complete .pac file image.
+ * finalState (host, may be NULL): [S][2] = (huffman.bitDeposit, cp.extraBits) at end of stream. */
+int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S,
+                     uint8_t *out, int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace);
+
+/* replaces the Decode pass of pacfile.py:430-499: PACFile.ReadFileHeader/ReadDataBlock (pacfile.py:123-229),
+ * Huffman.decodeData (Huffman.py:321-344), codec.Decode (codec.py:25-65), overlap-add, first block dropped
+ * (pacfile.py:485-487), tail emitted (:171-176), PCMFile.WriteDataBlock quantisation (pcmfile.py:118-147).
+ * pac: concatenated file images, stream s = pac[pacOff[s] .. pacOff[s+1]) (pacOff host; pac host or device).
+ * pcm: interleaved int16 [S][strideSamples][2], host or device; nSamplesOut[s] (host) = samples/channel written;
+ * hdrNumSamples/hdrSampleRate (host, may be NULL) = header fields (the WAV header uses them, pcmfile.py:103-116). */
+int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,
+                     int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate);
+/* upper bound of samples/channel a .pac image of nbytes can decode to */
+int64_t pac_decode_bound(PacCtx *ctx, int64_t nbytes);
+
+/* ------------------------------------------------------------------ per-block API (codec.Encode / codec.Decode) */
+/* Mutable per-stream state the reference keeps on CodingParams / Huffman objects */
+typedef struct {
+    int64_t extraBits;    /* cp.extraBits      pacfile.py:269, codec.py:229,260 */
+    int64_t bitDeposit;   /* huffman.bitDeposit Huffman.py:262,353-371 */
+} PacStreamState;
+
+/* codec.Encode(data, codingParams, huffman) (codec.py:83-129) on nblk independent (state, block) pairs.
+ * data [nblk][2][2*nMDCTLines] signed fractions (prior|current, NOT windowed; unlike the reference the
+ * caller's array is not modified).  Outputs (host):
+ *   scaleFactor,bitAlloc [nblk][2][nBands]; mant [nblk][2][nMDCTLines] signed mantissa codes at their line
+ *   positions (0 where bitAlloc==0); tableID, overallScale [nblk][2]; lrms [nblk] bit mask;
+ *   chunk (may be NULL) [nblk][2][chunkCap] packed payload as WriteDataBlock writes it (pacfile.py:319-351),
+ *   chunkBytes [nblk][2].  state[nblk] is updated in place. */
+int pac_encode_blocks(PacCtx *ctx, const double *data, int nblk, PacStreamState *state,
+                      int32_t *scaleFactor, int32_t *bitAlloc, int32_t *mant, int32_t *tableID,
+                      int32_t *overallScale, int32_t *lrms, uint8_t *chunk, int64_t chunkCap, int32_t *chunkBytes);
+
+/* codec.Decode(scaleFactor, bitAlloc, mantissa, overallScaleFactor, codingParams, LRMS) (codec.py:25-65).
+ * mant [nblk][2][nMDCTLines] signed codes at line positions; out [nblk][2][2*nMDCTLines] windowed IMDCT output
+ * (pre overlap-add), including the decoder's M/S aliasing quirk (codec.py:46-56). */
+int pac_decode_blocks(PacCtx *ctx, const int32_t *scaleFactor, const int32_t *bitAlloc, const int32_t *mant,
+                      const int32_t *overallScale, const int32_t *lrms, int nblk, double *out);
+/* parse nblk (2-channel) chunks as ReadDataBlock does (pacfile.py:167-217, Huffman.py:321-344).
+ * chunks: [nblk][2][chunkCap] payloads, chunkBytes [nblk][2]. */
+int pac_unpack_blocks(PacCtx *ctx, const uint8_t *chunks, int64_t chunkCap, const int32_t *chunkBytes, int nblk,
+                      int32_t *scaleFactor, int32_t *bitAlloc, int32_t *mant, int32_t *overallScale, int32_t *lrms,
+                      int32_t *tableID);
+
+/* ------------------------------------------------------------------ L2 entry points (reference function names) */
+/* window.py:27-39 SineWindow (kind 0), :41-53 HanningWindow (1), :56-78 KBDWindow alpha=4 (2); x [n][N] in place */
+int pac_window(PacCtx *ctx, int kind, double *x, int n, int N);
+/* mdct.py:49-71 MDCT(data, N/2, N/2): x [n][N] -> X [n][N/2];  mdct.py:73-88 IMDCT: X [n][N/2] -> x [n][N] */
+int pac_mdct(PacCtx *ctx, const double *x, int n, int N, double *X);
+int pac_imdct(PacCtx *ctx, const double *X, int n, int N, double *x);
+/* the analysis stage on nblk raw blocks: codec.py:96-102 (LRMS) + :237-246 (window, MDCT, overall scale) +
+ * psychoac.getStereoMaskThreshold (psychoac.py:506-682).  data [nblk][2][N] raw signed fractions.
+ * mdct [nblk][2][N/2] scaled L/R lines, bthr [nblk][6][N/2] (L,R,M,S,M',S' thresholds, dB), smr [nblk][2][nBands],
+ * lines [nblk][2][N/2] LRMS-selected lines; any output may be NULL. */
+int pac_analysis(PacCtx *ctx, const double *data, int nblk, int32_t *lrms, int32_t *oscale, double *mdct,
+                 double *bthr, double *smr, double *lines);
+/* psychoac.CalcSMRs (psychoac.py:253-318), mono: data [n][N] time samples (window NOT yet applied; the reference
+ * applies Hann itself), mdct [n][N/2] lines scaled by 2^scale, -> smr [n][nBands] */
+int pac_calc_smrs(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr);
+/* bitalloc.BitAlloc (bitalloc.py:129-184) on n independent problems */
+int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *extraBits, int maxMantBits,
+                 const double *smr /*[n][nBands]*/, const int32_t *lrms /*[n] masks*/, int32_t *bits /*[n][nBands]*/,
+                 int64_t *bitDifference /*[n]*/);
+/* quantize.py: ScaleFactor :148-177 (n scalars), vQuantizeUniform :91-117, vDequantizeUniform :120-145,
+ * vMantissa :315-342, vDequantize :345-376 */
+int pac_scale_factor(PacCtx *ctx, const double *x, int n, int nScaleBits, int nMantBits, int32_t *scale);
+int pac_vquantize_uniform(PacCtx *ctx, const double *x, int n, int nBits, uint64_t *q);
+int pac_vdequantize_uniform(PacCtx *ctx, const uint64_t *q, int n, int nBits, double *x);
+int pac_vmantissa(PacCtx *ctx, const double *x, int n, int scale, int nScaleBits, int nMantBits, uint64_t *m);
+int pac_vdequantize(PacCtx *ctx, int scale, const int64_t *m, int n, int nScaleBits, int nMantBits, double *x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,457 @@
+// analysis.cuh -- K1+K2+K3 fused: one CTA per stereo block does
+//   PCM -> signed fractions (pcmfile.py:66-100, quantize.py:120-145)
+//   raw-FFT M/S decision per band (codec.py:96-102)
+//   SineWindow + MDCT + overall scale (codec.py:237-246, window.py:27-39, mdct.py:49-71, quantize.py:148-177)
+//   getStereoMaskThreshold (psychoac.py:506-682): six masked-threshold curves (calcBTHR :409-456,
+//   findpeaks :158-191, Masker :66-120), MLD (:349-372), per-band max SMR (:458-504), LRMS select (:662-682)
+// entirely out of shared memory / registers; HBM traffic is the algorithmic 4 KB in + ~8.6 KB out per block.
+//
+// The algebra (real FFTs via packed complex FFTs, MDCT via fold + M/2-point FFT, Hann^p windows of the
+// M/S signals as 3-tap frequency-domain convolutions) is stated in numpy in tests/model_analysis.py and
+// checked there against dumps of the reference.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace pac {
+
+template <typename T>
+struct AnalysisArgs {
+    // ---- input: exactly one of pcm / blocks
+    const int16_t *pcm;          // [S][strideSamples][2]
+    int64_t strideSamples;
+    const int64_t *nSamples;     // [S]
+    const double *blocks;        // [nwork][2][N] raw signed fractions
+    int S, b0, nb;               // work item w: stream s = w / nb, block b = b0 + w % nb
+    int64_t nwork;
+    int nScaleBits;
+    // ---- outputs, indexed by w
+    T *lines;                    // [nwork][2][M]  LRMS-selected scaled lines
+    T *smr;                      // [nwork][2][kMaxBands]
+    T *bmax;                     // [nwork][2][kMaxBands] max |selected line| per band
+    uint8_t *oscale;             // [nwork][2]
+    uint32_t *lrms;              // [nwork]
+    T *dbg_mdct;                 // [nwork][2][M]  (optional) scaled L/R lines
+    T *dbg_bthr;                 // [nwork][6][M]  (optional) L,R,M,S,M',S' thresholds in dB
+    DevTables<T> tab;
+    BandInfo bands;
+};
+
+template <typename T, int LOGM>
+struct AnalysisSmem {
+    static constexpr int M = 1 << LOGM;
+    static constexpr int N = 2 * M;
+    static constexpr int NT = M / 4;
+    using T2 = typename Vec2<T>::type;
+    T2 XF[2][M + 2];       // time samples x[ch][n] (viewed as T[2][N+4]); later F1[ch][0..M]
+    T2 W[2][M + 2];        // FFT work; later F2_M, F2_S; finally the four per-line SMR candidate arrays
+    T Lb[2][M];            // scaled MDCT lines L, R
+    T P[M + 8];            // |spectrum|^2 of the current curve
+    T mz[M / 2], mp[M / 2], ml[M / 2];   // masker list: Bark position, SPL, 0.367*max(SPL-40,0)
+    T red[64];
+    int wsum[NT / 32 + 1];
+    int cnt;
+    uint32_t lrms;
+    int oscale[2];
+};
+
+// spread + accumulate one masker into 4 lines.  fp64 keeps the reference's operation order
+// (psychoac.py:111-120); fp32 folds the constants and uses ex2.approx.
+__device__ __forceinline__ void spread4(double (&acc)[4], const double (&zl)[4], double zm, double pm, double lev, double drop) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double dz = zl[j] - zm;
+        double a = fabs(dz);
+        double spreadv = ((dz >= 0.0 ? lev : 0.0) - 27.0) * (a > 0.5 ? a - 0.5 : 0.0);
+        double spl = pm + spreadv - drop;
+        acc[j] += exp10((spl - 96.0) / 10.0);
+    }
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void spread4(float (&acc)[4], const float (&zl)[4], float zm, float pm, float lev, float drop) {
+    const float K = 0.33219280948873623f;           // log2(10)/10
+    float c0 = (pm - drop - 96.0f) * K;
+    float up = (lev - 27.0f) * K, dn = -27.0f * K;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float dz = zl[j] - zm;
+        float a = fmaxf(fabsf(dz) - 0.5f, 0.0f);
+        float sl = dz >= 0.0f ? up : dn;
+        acc[j] += ex2_approx(fmaf(sl, a, c0));
+    }
+}
+
+
+// DFT of hann*y at bin k (0 <= k < M) from F = DFT(y)[0..M], y real:  .5 F[k] - .25 (w F[k-1] + conj(w) F[k+1])
+template <typename T>
+__device__ __forceinline__ typename Vec2<T>::type hann_tap(const typename Vec2<T>::type *F, int k,
+                                                           typename Vec2<T>::type hw, typename Vec2<T>::type hwc) {
+    using T2 = typename Vec2<T>::type;
+    T2 fm = k == 0 ? cconj(F[1]) : F[k - 1];
+    T2 fp = F[k + 1];
+    T2 t = cadd(cmul(hw, fm), cmul(hwc, fp));
+    return mk2<T>((T)0.5 * F[k].x - (T)0.25 * t.x, (T)0.5 * F[k].y - (T)0.25 * t.y);
+}
+
+// One masked-threshold curve (calcBTHR body after the FFT, psychoac.py:431-456): power spectrum from `spec`,
+// findpeaks (:158-191), masker SPLs (:448), spreading over this thread's 4 lines (:447-452), + threshold in quiet,
+// -> dB.  All threads of the CTA must call; uses sm.P / sm.mz / sm.mp / sm.ml / sm.wsum / sm.cnt.
+template <typename T, int LOGM, class Spec>
+__device__ __forceinline__ void masked_curve(AnalysisSmem<T, LOGM> &sm, const DevTables<T> &tb, Spec spec, T drop,
+                                             const T (&zl)[4], const T (&tiq)[4], T (&thr)[4]) {
+    using T2 = typename Vec2<T>::type;
+    constexpr int M = 1 << LOGM, NT = M / 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int k = tid + NT * j;
+        T2 v = spec(k);
+        sm.P[k] = v.x * v.x + v.y * v.y;
+    }
+    __syncthreads();
+    // findpeaks on 4 consecutive bins per thread, ordered compaction
+    int k0 = 4 * tid;
+    unsigned flags = 0;
+    {
+        T pw[6];
+        pw[0] = k0 > 0 ? sm.P[k0 - 1] : (T)0;
+        pw[1] = sm.P[k0]; pw[2] = sm.P[k0 + 1]; pw[3] = sm.P[k0 + 2]; pw[4] = sm.P[k0 + 3];
+        pw[5] = k0 + 4 < M ? sm.P[k0 + 4] : (T)0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int k = k0 + q;
+            // |X[k]| > |X[k-1]|, |X[k]| > |X[k+1]|, 10 log10|X[k]| > -30  (:166-168), on squared magnitudes
+            bool pk = k >= 1 && k <= M - 2 && pw[q + 1] > pw[q] && pw[q + 1] > pw[q + 2] && pw[q + 1] > (T)1e-6;
+            flags |= pk ? (1u << q) : 0u;
+        }
+    }
+    int npk = __popc(flags);
+    int incl = npk;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    int offs = incl - npk;
+    for (int i = 0; i < warp; i++) offs += sm.wsum[i];
+    if (tid == NT - 1) sm.cnt = offs + npk;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (flags & (1u << q)) {
+            int k = k0 + q;
+            T ssum = 0;                                 // X_fft[k-3:k+3] with python slice semantics (:448)
+            if (k >= 3) {
+                int hi = k + 3 < M ? k + 3 : M;
+                for (int jj = k - 3; jj < hi; jj++) ssum += sm.P[jj];
+            }
+            T pmv = spl_of<T>(tb.cnorm * ssum);
+            T lv = (T)0.367 * (pmv - (T)40 > 0 ? pmv - (T)40 : (T)0);     // :114
+            sm.mz[offs] = tb.zpeak[k]; sm.mp[offs] = pmv; sm.ml[offs] = lv;
+            offs++;
+        }
+    }
+    __syncthreads();
+    const int cnt = sm.cnt;
+    T acc[4] = {0, 0, 0, 0};
+    for (int m = 0; m < cnt; m++) spread4(acc, zl, sm.mz[m], sm.mp[m], sm.ml[m], drop);
+#pragma unroll
+    for (int j = 0; j < 4; j++) thr[j] = spl_of<T>(acc[j] + tiq[j]);      // :454-456
+    __syncthreads();
+}
+
+template <typename T, int LOGM>
+__global__ void __launch_bounds__((1 << LOGM) / 4)
+k_analysis(const AnalysisArgs<T> a) {
+    using S = AnalysisSmem<T, LOGM>;
+    using T2 = typename Vec2<T>::type;
+    constexpr int M = S::M, N = S::N, NT = S::NT, H = M / 2, NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S &sm = *reinterpret_cast<S *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevTables<T> &tb = a.tab;
+    const int NB = a.bands.nBands;
+    T *xt = reinterpret_cast<T *>(&sm.XF[0][0]);      // x[ch][n] at xt[ch*(N+4) + n]
+    constexpr int XS = N + 4;
+
+    // per-thread constants for its 4 lines i = tid + NT*j
+    T zl[4], tiq[4], mld[4];
+    int bnd[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int i = tid + NT * j;
+        zl[j] = tb.zline[i]; tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
+    }
+
+    for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+        const int s = (int)(w / a.nb);
+        const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
+        // ------------------------------------------------ A. load one 2048-sample stereo window
+        if (a.pcm) {
+            const int64_t ns = a.nSamples[s];
+            const int64_t nblk = (ns + M - 1) / M + 1;
+            if (b >= nblk) continue;                     // uniform for the CTA
+            const int *p32 = reinterpret_cast<const int *>(a.pcm) + (int64_t)s * a.strideSamples;
+            const int64_t base = (int64_t)(b - 1) * M;
+#pragma unroll
+            for (int j = 0; j < N / NT; j++) {
+                int n = tid + NT * j;
+                int64_t si = base + n;
+                int v = (si >= 0 && si < ns) ? __ldg(p32 + si) : 0;
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    int c = ch ? (v >> 16) : (int)(short)(v & 0xffff);
+                    int code = c < 0 ? -c : c;
+                    if (code & 32768) code -= 32768;          // -32768 dequantises to 0 (quantize.py:133-138)
+                    T f = (T)(2 * code) / (T)65535;           // quantize.py:141
+                    xt[ch * XS + n] = c < 0 ? -f : f;
+                }
+            }
+        } else {
+            const double *src = a.blocks + w * 2 * N;
+#pragma unroll
+            for (int j = 0; j < 2 * N / NT; j++) {
+                int e = tid + NT * j;
+                int ch = e / N, n = e - ch * N;
+                xt[ch * XS + n] = (T)src[e];
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------ B. raw FFTs -> LRMS decision (codec.py:96-102)
+        for (int e = tid; e < 2 * M; e += NT) {
+            int ch = e / M, m = e - ch * M;
+            sm.W[ch][m] = sm.XF[ch][m];                   // (x[2m], x[2m+1])
+        }
+        if (tid == 0) sm.lrms = 0;
+        __syncthreads();
+        fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+        for (int bd = warp; bd < NB; bd += NW) {
+            T dr = 0, di = 0, sr = 0, si = 0;
+            for (int k = a.bands.lo[bd] + lane; k < a.bands.lo[bd + 1]; k += 32) {
+                T2 l = rfft_split<T, LOGM>(sm.W[0], k, tb.tw_split);
+                T2 r = rfft_split<T, LOGM>(sm.W[1], k, tb.tw_split);
+                T l2r = l.x * l.x - l.y * l.y, l2i = l.x * l.y + l.y * l.x;
+                T r2r = r.x * r.x - r.y * r.y, r2i = r.x * r.y + r.y * r.x;
+                dr += l2r - r2r; di += l2i - r2i;
+                sr += l2r + r2r; si += l2i + r2i;
+            }
+            dr = warp_sum(dr); di = warp_sum(di); sr = warp_sum(sr); si = warp_sum(si);
+            if (lane == 0) {
+                double dd = hypot((double)dr, (double)di), ss = hypot((double)sr, (double)si);
+                if (dd < 0.8 * ss) atomicOr(&sm.lrms, 1u << bd);
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
+        for (int e = tid; e < 2 * N; e += NT) {
+            int ch = e / N, n = e - ch * N;
+            xt[ch * XS + n] *= tb.sinw[n];
+        }
+        __syncthreads();
+        for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
+            int ch = e / H, n = e - ch * H;
+            const T *x = xt + ch * XS;
+            int m0 = 2 * n, m1 = M - 1 - 2 * n;
+            T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
+            T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
+            sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
+        }
+        __syncthreads();
+        fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
+        T mx[2] = {0, 0};
+        for (int e = tid; e < 2 * H; e += NT) {
+            int ch = e / H, k = e - ch * H;
+            T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+            T v0 = ((T)2 / (T)N) * y.x, v1 = -((T)2 / (T)N) * y.y;
+            sm.Lb[ch][2 * k] = v0;
+            sm.Lb[ch][M - 1 - 2 * k] = v1;
+            T m = fmax(fabs(v0), fabs(v1));
+            if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
+        }
+        mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
+        if (lane == 0) { sm.red[warp] = mx[0]; sm.red[32 + warp] = mx[1]; }
+        __syncthreads();
+        if (tid < 2) {
+            T m = 0;
+            for (int i = 0; i < NW; i++) m = fmax(m, sm.red[32 * tid + i]);
+            sm.oscale[tid] = scale_factor((double)m, a.nScaleBits, 5);   // codec.py:245: ScaleFactor(maxLine, nScaleBits) with the default nMantBits=5
+        }
+        __syncthreads();
+        const int osc0 = sm.oscale[0], osc1 = sm.oscale[1];
+        for (int e = tid; e < 2 * M; e += NT) {
+            int ch = e / M, i = e - ch * M;
+            sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
+        }
+        // ------------------------------------------------ D. Hann on the sine-windowed data (psychoac.py:428) + FFT
+        for (int e = tid; e < 2 * M; e += NT) {
+            int ch = e / M, m = e - ch * M;
+            T2 x2 = sm.XF[ch][m];
+            const T2 h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
+            sm.W[ch][m] = mk2<T>(x2.x * h2.x, x2.y * h2.y);
+        }
+        __syncthreads();
+        fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+        for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M
+            int ch = e / (M + 1), k = e - ch * (M + 1);
+            sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
+        }
+        __syncthreads();
+        // F2_M, F2_S = Hann-taps of (F1_L +- F1_R)/2   (psychoac.py:549 then :428 again)
+        const T2 hw = tb.hann_w, hwc = cconj(tb.hann_w);
+        for (int e = tid; e < 2 * (M + 1); e += NT) {
+            int c = e / (M + 1), k = e - c * (M + 1);
+            T sg = c ? (T)-1 : (T)1;
+            int km = k == 0 ? 1 : k - 1, kp = k == M ? M - 1 : k + 1;
+            T2 f0 = sm.XF[0][k], f1 = sm.XF[1][k];
+            T2 g0 = sm.XF[0][km], g1 = sm.XF[1][km];
+            T2 h0 = sm.XF[0][kp], h1 = sm.XF[1][kp];
+            T2 fc = mk2<T>((f0.x + sg * f1.x) / 2, (f0.y + sg * f1.y) / 2);
+            T2 fm = mk2<T>((g0.x + sg * g1.x) / 2, (g0.y + sg * g1.y) / 2);
+            T2 fp = mk2<T>((h0.x + sg * h1.x) / 2, (h0.y + sg * h1.y) / 2);
+            if (k == 0) fm = cconj(fm);
+            if (k == M) fp = cconj(fp);
+            T2 t = cadd(cmul(hw, fm), cmul(hwc, fp));
+            sm.W[c][k] = mk2<T>((T)0.5 * fc.x - (T)0.25 * t.x, (T)0.5 * fc.y - (T)0.25 * t.y);
+        }
+        __syncthreads();
+        // ------------------------------------------------ E. six masked-threshold curves
+        T thr[6][4];
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, tiq, thr[0]);   // BTHR_L  :540
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[1][k]; }, (T)15, zl, tiq, thr[1]);   // BTHR_R  :541
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[0][k]; }, (T)15, zl, tiq, thr[2]);    // BTHR_M  :559
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[1][k]; }, (T)15, zl, tiq, thr[3]);    // BTHR_S  :560
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[0], k, hw, hwc); }, (T)0, zl, tiq, thr[4]);   // :561
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, tiq, thr[5]);   // :562
+        // ------------------------------------------------ F. SMR candidates, band maxima, select
+        const uint32_t lrms = sm.lrms;
+        T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
+        T outl[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int i = tid + NT * j;
+            T xl = sm.Lb[0][i], xr = sm.Lb[1][i];
+            T xm = (xl + xr) / 2, xs = (xl - xr) / 2;                                     // psychoac.py:551
+            T sl = spl_of<T>((T)4 * (xl * xl)) - (T)6.02 * (T)osc0;                      // :534
+            T sr = spl_of<T>((T)4 * (xr * xr)) - (T)6.02 * (T)osc1;                      // :535
+            T sM = spl_of<T>((T)4 * (xm * xm)) - (T)6.02 * (T)osc0;                      // :554
+            T sS = spl_of<T>((T)4 * (xs * xs)) - (T)6.02 * (T)osc1;                      // :555
+            T mldM = thr[4][j] * mld[j], mldS = thr[5][j] * mld[j];                      // :582-583
+            T thrM = fmax(thr[2][j], fmin(thr[3][j], mldS));                             // :591
+            T thrS = fmax(thr[3][j], fmin(thr[2][j], mldM));
+            V[0 * M + i] = sl - thr[0][j];
+            V[1 * M + i] = sr - thr[1][j];
+            V[2 * M + i] = sM - thrM;
+            V[3 * M + i] = sS - thrS;
+            bool ms = (lrms >> bnd[j]) & 1u;
+            outl[0][j] = ms ? xm : xl;
+            outl[1][j] = ms ? xs : xr;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int i = tid + NT * j;
+            a.lines[(w * 2 + 0) * M + i] = outl[0][j];
+            a.lines[(w * 2 + 1) * M + i] = outl[1][j];
+        }
+        if (a.dbg_mdct) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int i = tid + NT * j;
+                a.dbg_mdct[(w * 2 + 0) * M + i] = sm.Lb[0][i];
+                a.dbg_mdct[(w * 2 + 1) * M + i] = sm.Lb[1][i];
+            }
+        }
+        if (a.dbg_bthr) {
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) a.dbg_bthr[(w * 6 + c) * M + tid + NT * j] = thr[c][j];
+        }
+        __syncthreads();
+        for (int bd = warp; bd < NB; bd += NW) {
+            const bool ms = (lrms >> bd) & 1u;
+            T v0 = -INFINITY, v1 = -INFINITY, m0 = 0, m1 = 0;
+            const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
+            for (int i = lo + lane; i < hi; i += 32) {
+                T xl = sm.Lb[0][i], xr = sm.Lb[1][i];
+                T c0 = ms ? (xl + xr) / 2 : xl, c1 = ms ? (xl - xr) / 2 : xr;
+                v0 = fmax(v0, V[(ms ? 2 : 0) * M + i]);
+                v1 = fmax(v1, V[(ms ? 3 : 1) * M + i]);
+                m0 = fmax(m0, fabs(c0)); m1 = fmax(m1, fabs(c1));
+            }
+            v0 = warp_max(v0); v1 = warp_max(v1); m0 = warp_max(m0); m1 = warp_max(m1);
+            if (lane == 0) {
+                if (hi == lo) { v0 = (T)-96; v1 = (T)-96; }                              // psychoac.py:496-498
+                a.smr[(w * 2 + 0) * kMaxBands + bd] = v0;
+                a.smr[(w * 2 + 1) * kMaxBands + bd] = v1;
+                a.bmax[(w * 2 + 0) * kMaxBands + bd] = m0;
+                a.bmax[(w * 2 + 1) * kMaxBands + bd] = m1;
+            }
+        }
+        if (tid == 0) {
+            a.lrms[w] = lrms;
+            a.oscale[w * 2 + 0] = (uint8_t)osc0;
+            a.oscale[w * 2 + 1] = (uint8_t)osc1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- mono CalcSMRs (psychoac.py:215-318)
+template <typename T>
+struct SmrMonoArgs {
+    const double *data;      // [n][N] time samples (Hann applied here, psychoac.py:225)
+    const double *mdct;      // [n][M] lines scaled by 2^scale
+    int n, scale;
+    double *smr;             // [n][kMaxBands]
+    double *thr;             // [n][M] optional masked threshold (getMaskedThreshold)
+    DevTables<T> tab;
+    BandInfo bands;
+};
+
+template <typename T, int LOGM>
+__global__ void __launch_bounds__((1 << LOGM) / 4)
+k_calc_smrs(const SmrMonoArgs<T> a) {
+    using S = AnalysisSmem<T, LOGM>;
+    using T2 = typename Vec2<T>::type;
+    constexpr int M = S::M, N = S::N, NT = S::NT, NW = NT / 32 > 0 ? NT / 32 : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S &sm = *reinterpret_cast<S *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevTables<T> &tb = a.tab;
+    T zl[4], tiq[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { zl[j] = tb.zline[tid + NT * j]; tiq[j] = tb.tiq[tid + NT * j]; }
+    const int w = blockIdx.x;
+    for (int m = tid; m < M; m += NT) {
+        T x0 = (T)a.data[(int64_t)w * N + 2 * m] * tb.hann[2 * m];
+        T x1 = (T)a.data[(int64_t)w * N + 2 * m + 1] * tb.hann[2 * m + 1];
+        sm.W[0][m] = mk2<T>(x0, x1);
+    }
+    __syncthreads();
+    fft_dif<T, LOGM, NT>(&sm.W[0][0], 1, M + 2, tb.tw, 1);
+    for (int k = tid; k <= M; k += NT) sm.XF[0][k] = rfft_split<T, LOGM>(sm.W[0], k, tb.tw_split);
+    __syncthreads();
+    T thr[4];
+    masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, tiq, thr);
+    T *V = reinterpret_cast<T *>(&sm.W[0][0]);
+    const T sc = (T)exp2((double)a.scale);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int i = tid + NT * j;
+        T tr = (T)a.mdct[(int64_t)w * M + i] / sc;                 // :285
+        V[i] = spl_of<T>((T)4 * (tr * tr)) - thr[j];                // :286-287, :316
+        if (a.thr) a.thr[(int64_t)w * M + i] = (double)thr[j];
+    }
+    __syncthreads();
+    for (int bd = warp; bd < a.bands.nBands; bd += NW) {
+        T v = -INFINITY;
+        const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
+        for (int i = lo + lane; i < hi; i += 32) v = fmax(v, V[i]);
+        v = warp_max(v);
+        if (lane == 0) a.smr[(int64_t)w * kMaxBands + bd] = hi > lo ? (double)v : 0.0;   // :309,314
+    }
+}
+
+}  // namespace pac

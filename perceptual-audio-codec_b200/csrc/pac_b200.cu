@@ -1,0 +1,1213 @@
+// pac_b200.cu -- C ABI (include/pac_b200.h) over the sm_100a kernels.  Host side: context, constant tables,
+// workspace, tiling of (streams x blocks), H2D/D2H staging.  No CPU fallback anywhere: every entry point
+// either launches kernels or fails with an error code.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "analysis.cuh"
+#include "common.cuh"
+#include "decode.cuh"
+#include "pack.cuh"
+#include "scan.cuh"
+#include "stages.cuh"
+
+using namespace pac;
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------ device buffer (grow-only)
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename U> U *as() { return reinterpret_cast<U *>(p); }
+};
+
+template <typename T>
+struct TableSet {
+    DevTables<T> dev;
+    void *mem = nullptr;
+};
+
+struct PacCtx {
+    int device = 0, precision = 0;
+    PacParams p{};
+    int M = 0, N = 0, LOGM = 0;
+    BandInfo bands{};
+    int32_t nLines[kMaxBands]{};
+    EncConsts ec{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int numSMs = 148;
+    // constant tables per N (the context's own N plus any N the L2 entry points were asked for)
+    std::map<int, TableSet<float>> tf;
+    std::map<int, TableSet<double>> td;
+    std::map<int, void *> winTables;      // key = kind*65536 + log2N
+    // Huffman
+    unsigned long long *lenLut = nullptr;
+    uint32_t *codeFlat = nullptr;
+    uint8_t *lenFlat = nullptr;
+    uint32_t *decLut = nullptr;
+    int32_t *trieChild = nullptr, *trieSym = nullptr;
+    DecodeTables dt{};
+    // workspaces
+    DBuf w_pcm, w_out, w_ns, w_state, w_lines, w_smr, w_bmax, w_osc, w_lrms, w_ba, w_sf, w_tid, w_nby, w_coff,
+        w_trE, w_trD, w_hdr, w_ovf, w_dbg1, w_dbg2, w_misc, w_misc2, w_misc3, w_misc4, w_misc5, w_misc6;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            char b_[512];                                                                         \
+            snprintf(b_, sizeof b_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = b_;                                                                        \
+            return PAC_E_CUDA;                                                                    \
+        }                                                                                         \
+    } while (0)
+
+#define FAIL(code, ...)                                   \
+    do {                                                  \
+        char b_[512];                                     \
+        snprintf(b_, sizeof b_, __VA_ARGS__);             \
+        ctx->err = b_;                                    \
+        return (code);                                    \
+    } while (0)
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+// ------------------------------------------------------------------ reference constants, computed in double
+// psychoac.py:56-64
+static double h_bark(double f) { double khz = f / 1000.0, t = khz / 7.5; return 13.0 * atan(khz * 0.76) + 3.5 * atan(t * t); }
+// psychoac.py:44-54
+static double h_thresh(double f) {
+    if (f < 10) f = 10;
+    double khz = f / 1000.0;
+    return 3.64 * pow(khz, -0.8) - 6.5 * exp(-0.6 * ((khz - 3.3) * (khz - 3.3))) + 0.001 * pow(khz, 4);
+}
+
+// psychoac.py:122-156 (cbFreqLimits, AssignMDCTLinesFromFreqLimits)
+static void h_band_layout(int nMDCTLines, int sampleRate, int32_t *nLines) {
+    static const double lim[25] = {100.0, 200.0, 300.0, 400.0, 510.0, 630.0, 770.0, 920.0, 1080.0, 1270.0, 1480.0, 1720.0, 2000.0,
+                                   2320.0, 2700.0, 3150.0, 3700.0, 4400.0, 5300.0, 6400.0, 7700.0, 9500.0, 12000.0, 15500.0, 24000.0};
+    double nyq_int = (double)(sampleRate / 2);      // `sampleRate / 2` with an int sampleRate under Python 2 (:133)
+    double lower = 0.0;
+    for (int b = 0; b < 25; b++) {
+        double upper = lim[b] >= sampleRate / 2.0 ? sampleRate / 2.0 : lim[b];
+        int cnt = 0;
+        for (int i = 0; i < nMDCTLines; i++) {
+            double f = (i + 0.5) / nMDCTLines * nyq_int;
+            if (f <= upper && f > lower) cnt++;
+        }
+        nLines[b] = cnt;
+        lower = upper;
+    }
+}
+
+template <typename T>
+static int build_tables(PacCtx *ctx, int N, TableSet<T> &ts) {
+    using T2 = typename Vec2<T>::type;
+    const int M = N / 2, H = M / 2, fs = ctx->p.sampleRate;
+    size_t nT = (size_t)N * 2 + (size_t)M * 4;
+    size_t nT2 = (size_t)M + (M + 1) + H + H;
+    size_t bytes = nT * sizeof(T) + nT2 * sizeof(T2) + M + 64;
+    std::vector<unsigned char> host(bytes);
+    T2 *t2 = reinterpret_cast<T2 *>(host.data());
+    T2 *tw = t2, *tws = tw + M, *pre = tws + (M + 1), *post = pre + H;
+    T *t1 = reinterpret_cast<T *>(post + H);
+    T *sinw = t1, *hann = sinw + N, *zline = hann + N, *tiq = zline + M, *mld = tiq + M, *zpeak = mld + M;
+    uint8_t *bol = reinterpret_cast<uint8_t *>(zpeak + M);
+    for (int m = 0; m < M; m++) { double a = -2.0 * M_PI * m / M; tw[m] = mk2<T>((T)cos(a), (T)sin(a)); }
+    for (int k = 0; k <= M; k++) { double a = -2.0 * M_PI * k / N; tws[k] = mk2<T>((T)cos(a), (T)sin(a)); }
+    for (int n = 0; n < H; n++) {
+        double a = -M_PI * n / M, b = -M_PI * (n + 0.25) / M;
+        pre[n] = mk2<T>((T)cos(a), (T)sin(a));
+        post[n] = mk2<T>((T)cos(b), (T)sin(b));
+    }
+    double Nf = (double)N;
+    for (int n = 0; n < N; n++) {
+        sinw[n] = (T)sin((n + 0.5) * M_PI / Nf);                                   // window.py:35-37
+        hann[n] = (T)(0.5 * (1 - cos(2.0 * (n + 0.5) * M_PI / Nf)));               // window.py:49-51
+    }
+    double mx = 0;
+    std::vector<double> mldd(M);
+    for (int i = 0; i < M; i++) {
+        double f = fs / 2.0 / M * (i + 0.5);                                       // psychoac.py:434
+        zline[i] = (T)h_bark(f);
+        tiq[i] = (T)pow(10.0, (h_thresh(f) - 96) / 10);                            // :437
+        double f2 = ((i + 0.5) / M) * (fs / 2.0);                                  // :570
+        mldd[i] = pow(10.0, 1.25 * (1 - cos(M_PI * (fmin(f2, 3000.) / 3000.)) - 2.5));   // :367
+        if (mldd[i] > mx) mx = mldd[i];
+        zpeak[i] = (T)h_bark((double)i * (double)(fs / N));                        // :186-188, integer fs/N
+    }
+    for (int i = 0; i < M; i++) mld[i] = (T)(mldd[i] / mx);                        // :370
+    memset(bol, 0, M);
+    if (M == ctx->M)
+        for (int b = 0; b < ctx->bands.nBands; b++)
+            for (int i = ctx->bands.lo[b]; i < ctx->bands.lo[b + 1]; i++) bol[i] = (uint8_t)b;
+    CK(cudaMalloc(&ts.mem, bytes));
+    CK(cudaMemcpy(ts.mem, host.data(), bytes, cudaMemcpyHostToDevice));
+    unsigned char *d = reinterpret_cast<unsigned char *>(ts.mem);
+    auto dv = [&](const void *hp) { return d + (reinterpret_cast<const unsigned char *>(hp) - host.data()); };
+    ts.dev.tw = reinterpret_cast<const T2 *>(dv(tw));
+    ts.dev.tw_split = reinterpret_cast<const T2 *>(dv(tws));
+    ts.dev.mdct_pre = reinterpret_cast<const T2 *>(dv(pre));
+    ts.dev.mdct_post = reinterpret_cast<const T2 *>(dv(post));
+    ts.dev.sinw = reinterpret_cast<const T *>(dv(sinw));
+    ts.dev.hann = reinterpret_cast<const T *>(dv(hann));
+    ts.dev.zline = reinterpret_cast<const T *>(dv(zline));
+    ts.dev.tiq = reinterpret_cast<const T *>(dv(tiq));
+    ts.dev.mld = reinterpret_cast<const T *>(dv(mld));
+    ts.dev.zpeak = reinterpret_cast<const T *>(dv(zpeak));
+    ts.dev.band_of_line = reinterpret_cast<const uint8_t *>(dv(bol));
+    ts.dev.hann_w = mk2<T>((T)cos(M_PI / N), (T)sin(M_PI / N));
+    ts.dev.cnorm = (T)(8.0 / 3.0 * 4.0 / ((double)N * (double)N));                 // psychoac.py:448
+    ts.dev.imdct_scale = (T)2;
+    return PAC_OK;
+}
+
+template <typename T> static std::map<int, TableSet<T>> &tabmap(PacCtx *ctx);
+template <> std::map<int, TableSet<float>> &tabmap<float>(PacCtx *ctx) { return ctx->tf; }
+template <> std::map<int, TableSet<double>> &tabmap<double>(PacCtx *ctx) { return ctx->td; }
+
+template <typename T>
+static int get_tables(PacCtx *ctx, int N, DevTables<T> *out) {
+    auto &m = tabmap<T>(ctx);
+    auto it = m.find(N);
+    if (it == m.end()) {
+        TableSet<T> ts;
+        int rc = build_tables<T>(ctx, N, ts);
+        if (rc) return rc;
+        it = m.emplace(N, ts).first;
+    }
+    *out = it->second.dev;
+    return PAC_OK;
+}
+
+// ------------------------------------------------------------------ Huffman tables -> device LUTs
+struct HostTrie {
+    std::vector<int32_t> child, sym;
+    int add() { child.push_back(-1); child.push_back(-1); sym.push_back(-2); return (int)sym.size() - 1; }
+};
+
+static int build_huffman(PacCtx *ctx, const PacHuffTables *h) {
+    int total = 0;
+    for (int t = 0; t < kNTables; t++) {
+        if (h->nkeys[t] <= 0 || h->nkeys[t] > kLenLutSize || h->esc_len[t] <= 0 || h->esc_len[t] > 24) FAIL(PAC_E_ARG, "bad Huffman table %d", t + 1);
+        ctx->ec.nkeys[t] = h->nkeys[t]; ctx->ec.off[t] = h->off[t];
+        ctx->ec.esc_len[t] = h->esc_len[t]; ctx->ec.esc_code[t] = h->esc_code[t];
+        if (h->off[t] + h->nkeys[t] > total) total = h->off[t] + h->nkeys[t];
+    }
+    std::vector<unsigned long long> lut(kLenLutSize, 0ull);
+    for (int t = 0; t < kNTables; t++)
+        for (int v = 0; v < h->nkeys[t]; v++) {
+            unsigned l = h->len[h->off[t] + v];
+            if (l > 31) FAIL(PAC_E_ARG, "Huffman code longer than 31 bits");
+            lut[v] |= (unsigned long long)l << (5 * t);
+        }
+    CK(cudaMalloc(&ctx->lenLut, lut.size() * 8));
+    CK(cudaMemcpy(ctx->lenLut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->codeFlat, (size_t)total * 4));
+    CK(cudaMemcpy(ctx->codeFlat, h->code, (size_t)total * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->lenFlat, (size_t)total));
+    CK(cudaMemcpy(ctx->lenFlat, h->len, (size_t)total, cudaMemcpyHostToDevice));
+    // decoder: binary tries (Huffman.py:321-344 does a string-prefix search; a trie is the same relation)
+    HostTrie tr;
+    int root[kNTables];
+    auto insert = [&](int r, uint32_t code, int len, int sym) {
+        int cur = r;
+        for (int i = len - 1; i >= 0; i--) {
+            int bit = (code >> i) & 1;
+            if (tr.child[2 * cur + bit] < 0) { int c = tr.add(); tr.child[2 * cur + bit] = c; }
+            cur = tr.child[2 * cur + bit];
+        }
+        tr.sym[cur] = sym;
+    };
+    for (int t = 0; t < kNTables; t++) {
+        root[t] = tr.add();
+        for (int v = 0; v < h->nkeys[t]; v++)
+            if (h->len[h->off[t] + v]) insert(root[t], h->code[h->off[t] + v], h->len[h->off[t] + v], v);
+        insert(root[t], h->esc_code[t], h->esc_len[t], -1);
+    }
+    std::vector<uint32_t> dl((size_t)kNTables << kLutBits);
+    for (int t = 0; t < kNTables; t++)
+        for (uint32_t pfx = 0; pfx < (1u << kLutBits); pfx++) {
+            int cur = root[t];
+            uint32_t e = 0;
+            bool done = false;
+            for (int d = 0; d < kLutBits; d++) {
+                if (tr.sym[cur] != -2) { e = kLutLeaf | ((uint32_t)(tr.sym[cur] + 1) << 8) | (uint32_t)d; done = true; break; }
+                int bit = (pfx >> (kLutBits - 1 - d)) & 1;
+                cur = tr.child[2 * cur + bit];
+                if (cur < 0) { e = kLutInvalid; done = true; break; }
+            }
+            if (!done) e = tr.sym[cur] != -2 ? (kLutLeaf | ((uint32_t)(tr.sym[cur] + 1) << 8) | (uint32_t)kLutBits) : (uint32_t)cur;
+            dl[((size_t)t << kLutBits) + pfx] = e;
+        }
+    CK(cudaMalloc(&ctx->decLut, dl.size() * 4));
+    CK(cudaMemcpy(ctx->decLut, dl.data(), dl.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->trieChild, tr.child.size() * 4));
+    CK(cudaMemcpy(ctx->trieChild, tr.child.data(), tr.child.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->trieSym, tr.sym.size() * 4));
+    CK(cudaMemcpy(ctx->trieSym, tr.sym.data(), tr.sym.size() * 4, cudaMemcpyHostToDevice));
+    ctx->dt.lut = ctx->decLut; ctx->dt.child = ctx->trieChild; ctx->dt.sym = ctx->trieSym;
+    for (int t = 0; t < kNTables; t++) ctx->dt.root[t] = root[t];
+    return PAC_OK;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" const char *pac_version(void) { return "pac-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *pac_last_error(PacCtx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t pac_launch_count(PacCtx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *params, const PacHuffTables *tables) {
+    if (!params || !tables) FAIL(PAC_E_ARG, "null params/tables");
+    if (precision != PAC_PRECISION_FP64 && precision != PAC_PRECISION_FP32) FAIL(PAC_E_ARG, "precision must be 0 (fp64) or 1 (fp32)");
+    if (params->nChannels != 2) FAIL(PAC_E_ARG, "only 2 channels are supported (as in the reference, codec.py:46-47)");
+    if (params->nMDCTLines != 1024 && params->nMDCTLines != 512) FAIL(PAC_E_ARG, "nMDCTLines must be 1024 or 512");
+    if (params->nScaleBits < 1 || params->nScaleBits > 4 || params->nMantSizeBits < 1 || params->nMantSizeBits > 4 ||
+        params->nTableIDBits < 4 || params->nTableIDBits > 8)
+        FAIL(PAC_E_ARG, "unsupported bit-field widths");
+    if (params->sampleRate < 8000 || params->sampleRate > 192000) FAIL(PAC_E_ARG, "unsupported sample rate");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(PAC_E_NODEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (device < 0 || device >= ndev) FAIL(PAC_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) FAIL(PAC_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    ctx->numSMs = prop.multiProcessorCount;
+    ctx->device = device; ctx->precision = precision; ctx->p = *params;
+    ctx->M = params->nMDCTLines; ctx->N = 2 * ctx->M; ctx->LOGM = ilog2(ctx->M);
+    h_band_layout(ctx->M, params->sampleRate, ctx->nLines);
+    ctx->bands.nBands = 25;
+    int lo = 0;
+    for (int b = 0; b < 25; b++) { ctx->bands.lo[b] = (int16_t)lo; lo += ctx->nLines[b]; }
+    for (int b = 25; b <= kMaxBands; b++) ctx->bands.lo[b] = (int16_t)lo;
+    if (lo != ctx->M) FAIL(PAC_E_ARG, "band layout does not cover the MDCT lines (%d of %d)", lo, ctx->M);
+    EncConsts &ec = ctx->ec;
+    const int NB = ctx->bands.nBands;
+    double bb = params->targetBitsPerSample * ctx->M;     // codec.py:223
+    bb -= params->nScaleBits * (NB + 1);                  // :224
+    bb -= params->nMantSizeBits * NB;                     // :225
+    bb -= params->nTableIDBits;                           // :227
+    ec.bitBudget = bb;
+    ec.nScaleBits = params->nScaleBits; ec.nMantSizeBits = params->nMantSizeBits; ec.nTableIDBits = params->nTableIDBits;
+    ec.maxMantBits = (1 << params->nMantSizeBits) > 16 ? 16 : (1 << params->nMantSizeBits);     // codec.py:218-219
+    ec.fixedBits = params->nScaleBits + params->nTableIDBits + NB * (params->nMantSizeBits + params->nScaleBits) + NB;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int rc = build_huffman(ctx, tables);
+    if (rc) return rc;
+    DevTables<float> tf; DevTables<double> td;
+    if ((rc = get_tables<float>(ctx, ctx->N, &tf))) return rc;
+    if ((rc = get_tables<double>(ctx, ctx->N, &td))) return rc;
+    return PAC_OK;
+}
+
+extern "C" int pac_ctx_create(int device, int precision, const PacParams *params, const PacHuffTables *tables, PacCtx **out) {
+    if (!out) return PAC_E_ARG;
+    *out = nullptr;
+    PacCtx *ctx = new PacCtx();
+    int rc = ctx_init(ctx, device, precision, params, tables);
+    if (rc) { g_create_error = ctx->err; pac_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return PAC_OK;
+}
+
+extern "C" void pac_ctx_destroy(PacCtx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
+    for (auto &kv : ctx->td) cudaFree(kv.second.mem);
+    for (auto &kv : ctx->winTables) cudaFree(kv.second);
+    cudaFree(ctx->lenLut); cudaFree(ctx->codeFlat); cudaFree(ctx->lenFlat);
+    cudaFree(ctx->decLut); cudaFree(ctx->trieChild); cudaFree(ctx->trieSym);
+    DBuf *bufs[] = {&ctx->w_pcm, &ctx->w_out, &ctx->w_ns, &ctx->w_state, &ctx->w_lines, &ctx->w_smr, &ctx->w_bmax, &ctx->w_osc,
+                    &ctx->w_lrms, &ctx->w_ba, &ctx->w_sf, &ctx->w_tid, &ctx->w_nby, &ctx->w_coff, &ctx->w_trE, &ctx->w_trD,
+                    &ctx->w_hdr, &ctx->w_ovf, &ctx->w_dbg1, &ctx->w_dbg2, &ctx->w_misc, &ctx->w_misc2, &ctx->w_misc3,
+                    &ctx->w_misc4, &ctx->w_misc5, &ctx->w_misc6};
+    for (DBuf *b : bufs) b->release();
+    delete ctx;
+}
+
+extern "C" int pac_band_layout(PacCtx *ctx, int32_t *nLines, int32_t *nBands) {
+    if (!ctx || !nLines || !nBands) return PAC_E_ARG;
+    for (int b = 0; b < ctx->bands.nBands; b++) nLines[b] = ctx->nLines[b];
+    *nBands = ctx->bands.nBands;
+    return PAC_OK;
+}
+
+extern "C" int64_t pac_num_blocks(PacCtx *ctx, int64_t nSamples) {
+    if (!ctx || nSamples < 0) return PAC_E_ARG;
+    return (nSamples + ctx->M - 1) / ctx->M + 1;
+}
+
+static int header_bytes(PacCtx *ctx) { return 4 + 18 + 4 + 2 * ctx->bands.nBands; }
+
+extern "C" int64_t pac_encode_bound(PacCtx *ctx, int64_t nSamples) {
+    if (!ctx || nSamples < 0) return PAC_E_ARG;
+    // target rate + a generous reservoir allowance; K5 refuses to write past the capacity it is given.
+    int64_t nb = pac_num_blocks(ctx, nSamples);
+    double perCh = ctx->p.targetBitsPerSample * ctx->M * 1.5 + 2048;
+    int64_t perBlock = 2 * (4 + (int64_t)(perCh / 8) + 1);
+    return header_bytes(ctx) + nb * perBlock + 4096;
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// pacfile.py:237-261
+static void build_header(PacCtx *ctx, int64_t nSamples, uint8_t *h) {
+    auto le32 = [](uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; };
+    auto le16 = [](uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; };
+    memcpy(h, "PAC ", 4);
+    uint32_t ns = (uint32_t)nSamples;
+    if (nSamples % ctx->M == 0) ns += ctx->M;            // :240-242 (the padding rule as written)
+    le32(h + 4, (uint32_t)ctx->p.sampleRate);
+    le16(h + 8, (uint32_t)ctx->p.nChannels);
+    le32(h + 10, ns);
+    le32(h + 14, (uint32_t)ctx->M);
+    le16(h + 18, (uint32_t)ctx->p.nScaleBits);
+    le16(h + 20, (uint32_t)ctx->p.nMantSizeBits);
+    le32(h + 22, (uint32_t)ctx->bands.nBands);
+    for (int b = 0; b < ctx->bands.nBands; b++) le16(h + 26 + 2 * b, (uint32_t)ctx->nLines[b]);
+}
+
+// ------------------------------------------------------------------ kernel launch helpers
+template <typename T, int LOGM>
+static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
+    size_t smem = sizeof(AnalysisSmem<T, LOGM>);
+    static bool configured[2] = {false, false};
+    (void)configured;
+    CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSM = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM>, (1 << LOGM) / 4, smem));
+    if (perSM < 1) perSM = 1;
+    int64_t grid = (int64_t)ctx->numSMs * perSM;
+    if (grid > a.nwork) grid = a.nwork;
+    if (grid < 1) grid = 1;
+    k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
+template <typename T>
+static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
+    a.bands = ctx->bands;
+    a.nScaleBits = ctx->p.nScaleBits;
+    int rc = get_tables<T>(ctx, ctx->N, &a.tab);
+    if (rc) return rc;
+    if (ctx->LOGM == 10) return launch_analysis_t<T, 10>(ctx, a);
+    if (ctx->LOGM == 9) return launch_analysis_t<T, 9>(ctx, a);
+    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+}
+
+template <typename T>
+static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
+    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.lenLut = ctx->lenLut;
+    constexpr int WARPS = 4;
+    k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
+template <typename T>
+static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
+    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.codeLut = ctx->codeFlat; a.lenLutFlat = ctx->lenFlat;
+    int64_t nchunks = (int64_t)a.S * a.nb * 2;
+    int64_t grid = (nchunks + kPackWarps - 1) / kPackWarps;
+    int64_t maxg = (int64_t)ctx->numSMs * 8;
+    if (grid > maxg) grid = maxg;
+    if (grid < 1) grid = 1;
+    k_pack<T><<<(unsigned)grid, kPackWarps * 32, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
+// ------------------------------------------------------------------ encode (whole streams)
+template <typename T>
+static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const int64_t *nSamples, int S, uint8_t *out,
+                          int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace) {
+    const int M = ctx->M, NB = ctx->bands.nBands, hdrB = header_bytes(ctx);
+    const bool pcmDev = is_device_ptr(pcm), outDev = is_device_ptr(out);
+    int64_t maxBlocksAll = 0;
+    for (int s = 0; s < S; s++) {
+        if (nSamples[s] < 0 || nSamples[s] > stride) FAIL(PAC_E_ARG, "nSamples[%d]=%lld outside [0, strideSamples]", s, (long long)nSamples[s]);
+        int64_t nb = pac_num_blocks(ctx, nSamples[s]);
+        if (nb > maxBlocksAll) maxBlocksAll = nb;
+    }
+    if (cap < hdrB) FAIL(PAC_E_OVERFLOW, "cap smaller than the file header");
+    // streams are processed in groups so that staging + intermediates stay bounded
+    const int64_t workBudget = 1 << 18;                       // (stream, block) items resident at once
+    int Sg = S;
+    const int64_t stagingLimit = (int64_t)24 << 30;
+    if (!pcmDev) { int64_t per = stride * 4 + (outDev ? 0 : cap); int64_t lim = stagingLimit / (per > 0 ? per : 1); if (lim < 1) lim = 1; if (Sg > lim) Sg = (int)lim; }
+    if (Sg > 8192) Sg = 8192;
+    int status = PAC_OK;
+    for (int s0 = 0; s0 < S; s0 += Sg) {
+        const int Sc = (S - s0 < Sg) ? S - s0 : Sg;
+        int64_t maxBlocks = 0;
+        for (int s = 0; s < Sc; s++) { int64_t nb = pac_num_blocks(ctx, nSamples[s0 + s]); if (nb > maxBlocks) maxBlocks = nb; }
+        int TB = (int)(workBudget / Sc);
+        if (TB < 8) TB = 8;
+        if (TB > maxBlocks) TB = (int)maxBlocks;
+        if (trace) TB = (int)maxBlocks;                      // taps are copied out once per group
+        const int64_t nwork = (int64_t)Sc * TB;
+        // ---- inputs
+        const int16_t *d_pcm;
+        if (pcmDev) d_pcm = pcm + (int64_t)s0 * stride * 2;
+        else {
+            CK(ctx->w_pcm.ensure((size_t)Sc * stride * 4 + 16));
+            CK(cudaMemcpyAsync(ctx->w_pcm.p, pcm + (int64_t)s0 * stride * 2, (size_t)Sc * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_pcm = ctx->w_pcm.as<int16_t>();
+        }
+        uint8_t *d_out;
+        if (outDev) d_out = out + (int64_t)s0 * cap;
+        else { CK(ctx->w_out.ensure((size_t)Sc * cap)); d_out = ctx->w_out.as<uint8_t>(); }
+        CK(ctx->w_ns.ensure((size_t)Sc * 8));
+        CK(cudaMemcpyAsync(ctx->w_ns.p, nSamples + s0, (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<StreamState> st(Sc);
+        for (int s = 0; s < Sc; s++) { st[s].extraBits = 0; st[s].bitDeposit = 0; st[s].outOffset = hdrB; st[s].reserved = 0; }   // pacfile.py:269, Huffman.py:262
+        CK(ctx->w_state.ensure((size_t)Sc * sizeof(StreamState)));
+        CK(cudaMemcpyAsync(ctx->w_state.p, st.data(), (size_t)Sc * sizeof(StreamState), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint8_t> hdr((size_t)Sc * hdrB);
+        for (int s = 0; s < Sc; s++) build_header(ctx, nSamples[s0 + s], hdr.data() + (size_t)s * hdrB);
+        CK(ctx->w_hdr.ensure(hdr.size()));
+        CK(cudaMemcpyAsync(ctx->w_hdr.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx->w_ovf.ensure((size_t)Sc * 4));
+        CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)Sc * 4, ctx->stream));
+        // ---- intermediates
+        CK(ctx->w_lines.ensure((size_t)nwork * 2 * M * sizeof(T)));
+        CK(ctx->w_smr.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+        CK(ctx->w_bmax.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+        CK(ctx->w_osc.ensure((size_t)nwork * 2));
+        CK(ctx->w_lrms.ensure((size_t)nwork * 4));
+        CK(ctx->w_ba.ensure((size_t)nwork * 2 * kMaxBands));
+        CK(ctx->w_sf.ensure((size_t)nwork * 2 * kMaxBands));
+        CK(ctx->w_tid.ensure((size_t)nwork * 2));
+        CK(ctx->w_nby.ensure((size_t)nwork * 2 * 4));
+        CK(ctx->w_coff.ensure((size_t)nwork * 2 * 8));
+        if (trace) { CK(ctx->w_trE.ensure((size_t)nwork * 8)); CK(ctx->w_trD.ensure((size_t)nwork * 8)); }
+        for (int b0 = 0; b0 < maxBlocks; b0 += TB) {
+            const int nb = (maxBlocks - b0 < TB) ? (int)(maxBlocks - b0) : TB;
+            AnalysisArgs<T> aa{};
+            aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.as<int64_t>(); aa.blocks = nullptr;
+            aa.S = Sc; aa.b0 = b0; aa.nb = nb; aa.nwork = (int64_t)Sc * nb;
+            aa.lines = ctx->w_lines.as<T>(); aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>();
+            aa.oscale = ctx->w_osc.as<uint8_t>(); aa.lrms = ctx->w_lrms.as<uint32_t>();
+            aa.dbg_mdct = nullptr; aa.dbg_bthr = nullptr;
+            int rc = launch_analysis<T>(ctx, aa);
+            if (rc) return rc;
+            ScanArgs<T> sa{};
+            sa.S = Sc; sa.b0 = b0; sa.nb = nb; sa.nSamples = ctx->w_ns.as<int64_t>(); sa.state = ctx->w_state.as<StreamState>();
+            sa.lines = aa.lines; sa.smr = aa.smr; sa.bmax = aa.bmax; sa.lrms = aa.lrms;
+            sa.ba = ctx->w_ba.as<uint8_t>(); sa.sf = ctx->w_sf.as<uint8_t>(); sa.tableID = ctx->w_tid.as<uint8_t>();
+            sa.nbytes = ctx->w_nby.as<uint32_t>(); sa.chunkOff = ctx->w_coff.as<long long>();
+            sa.trExtra = trace ? ctx->w_trE.as<long long>() : nullptr; sa.trDeposit = trace ? ctx->w_trD.as<long long>() : nullptr;
+            if ((rc = launch_scan<T>(ctx, sa))) return rc;
+            PackArgs<T> pa{};
+            pa.S = Sc; pa.b0 = b0; pa.nb = nb; pa.nSamples = ctx->w_ns.as<int64_t>();
+            pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
+            pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = d_out; pa.cap = cap; pa.perChunk = 0;
+            pa.overflow = ctx->w_ovf.as<int>(); pa.o_mant = nullptr;
+            pa.header = ctx->w_hdr.as<uint8_t>(); pa.headerBytes = hdrB;
+            if ((rc = launch_pack<T>(ctx, pa))) return rc;
+            if (trace) {      // single tile (TB == maxBlocks): copy the taps of this stream group
+                CK(cudaStreamSynchronize(ctx->stream));
+                const int64_t B = maxBlocksAll;
+                std::vector<T> hl, hs;
+                std::vector<uint8_t> hba((size_t)nwork * 2 * kMaxBands), hsf((size_t)nwork * 2 * kMaxBands), htid((size_t)nwork * 2), hosc((size_t)nwork * 2);
+                std::vector<uint32_t> hlr(nwork), hnby((size_t)nwork * 2);
+                std::vector<long long> hE(nwork), hD(nwork);
+                if (trace->lines) { hl.resize((size_t)nwork * 2 * M); CK(cudaMemcpy(hl.data(), aa.lines, hl.size() * sizeof(T), cudaMemcpyDeviceToHost)); }
+                if (trace->smr) { hs.resize((size_t)nwork * 2 * kMaxBands); CK(cudaMemcpy(hs.data(), aa.smr, hs.size() * sizeof(T), cudaMemcpyDeviceToHost)); }
+                CK(cudaMemcpy(hba.data(), sa.ba, hba.size(), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hsf.data(), sa.sf, hsf.size(), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(htid.data(), sa.tableID, htid.size(), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hosc.data(), aa.oscale, hosc.size(), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hlr.data(), aa.lrms, hlr.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hnby.data(), sa.nbytes, hnby.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hE.data(), sa.trExtra, hE.size() * 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hD.data(), sa.trDeposit, hD.size() * 8, cudaMemcpyDeviceToHost));
+                for (int s = 0; s < Sc; s++) {
+                    int64_t nbs = pac_num_blocks(ctx, nSamples[s0 + s]);
+                    for (int64_t b = 0; b < nbs; b++) {
+                        int64_t w = (int64_t)s * nb + b, g = (int64_t)(s0 + s) * B + b;
+                        if (trace->lrms) trace->lrms[g] = (int32_t)hlr[w];
+                        if (trace->extraBits) trace->extraBits[g] = hE[w];
+                        if (trace->bitDeposit) trace->bitDeposit[g] = hD[w];
+                        for (int ch = 0; ch < 2; ch++) {
+                            if (trace->oscale) trace->oscale[g * 2 + ch] = hosc[w * 2 + ch];
+                            if (trace->tableID) trace->tableID[g * 2 + ch] = htid[w * 2 + ch];
+                            if (trace->nbytes) trace->nbytes[g * 2 + ch] = (int32_t)hnby[w * 2 + ch];
+                            for (int bd = 0; bd < NB; bd++) {
+                                if (trace->ba) trace->ba[(g * 2 + ch) * NB + bd] = hba[(w * 2 + ch) * kMaxBands + bd];
+                                if (trace->sf) trace->sf[(g * 2 + ch) * NB + bd] = hsf[(w * 2 + ch) * kMaxBands + bd];
+                                if (trace->smr) trace->smr[(g * 2 + ch) * NB + bd] = (double)hs[(w * 2 + ch) * kMaxBands + bd];
+                            }
+                            if (trace->lines)
+                                for (int i = 0; i < M; i++) trace->lines[(g * 2 + ch) * M + i] = (double)hl[(w * 2 + ch) * M + i];
+                        }
+                    }
+                }
+            }
+        }
+        // ---- results of this group
+        CK(cudaMemcpyAsync(st.data(), ctx->w_state.p, (size_t)Sc * sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<int> ovf(Sc);
+        CK(cudaMemcpyAsync(ovf.data(), ctx->w_ovf.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int64_t maxBytes = 0;
+        for (int s = 0; s < Sc; s++) {
+            outBytes[s0 + s] = st[s].outOffset;
+            if (finalState) { finalState[(s0 + s) * 2] = st[s].bitDeposit; finalState[(s0 + s) * 2 + 1] = st[s].extraBits; }
+            if (ovf[s] || st[s].outOffset > cap) { status = PAC_E_OVERFLOW; outBytes[s0 + s] = -st[s].outOffset; }
+            else if (st[s].outOffset > maxBytes) maxBytes = st[s].outOffset;
+        }
+        if (!outDev && maxBytes > 0) {
+            CK(cudaMemcpy2DAsync(out + (int64_t)s0 * cap, (size_t)cap, d_out, (size_t)cap, (size_t)maxBytes, (size_t)Sc, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (status == PAC_E_OVERFLOW) ctx->err = "output capacity too small for at least one stream (outBytes[s] = -needed)";
+    return status;
+}
+
+extern "C" int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S,
+                                uint8_t *out, int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace) {
+    if (!ctx) return PAC_E_ARG;
+    if (!pcm || !nSamples || !out || !outBytes || S <= 0 || strideSamples < 0) FAIL(PAC_E_ARG, "bad arguments to pac_encode_batch");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return encode_batch_t<double>(ctx, pcm, strideSamples, nSamples, S, out, cap, outBytes, finalState, trace);
+    return encode_batch_t<float>(ctx, pcm, strideSamples, nSamples, S, out, cap, outBytes, finalState, trace);
+}
+
+// ------------------------------------------------------------------ decode (whole streams)
+extern "C" int64_t pac_decode_bound(PacCtx *ctx, int64_t nbytes) {
+    if (!ctx || nbytes < 0) return PAC_E_ARG;
+    int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
+    return (nbytes / minBlock + 2) * ctx->M;
+}
+
+template <typename T, int LOGM>
+static int launch_synth_t(PacCtx *ctx, SynthArgs<T> &a, int64_t grid) {
+    size_t smem = sizeof(SynthSmem<T, LOGM>);
+    CK(cudaFuncSetAttribute(k_synth<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_synth<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
+template <typename T>
+static int launch_synth(PacCtx *ctx, SynthArgs<T> &a, int64_t grid) {
+    a.bands = ctx->bands;
+    int rc = get_tables<T>(ctx, ctx->N, &a.tab);
+    if (rc) return rc;
+    if (ctx->LOGM == 10) return launch_synth_t<T, 10>(ctx, a, grid);
+    if (ctx->LOGM == 9) return launch_synth_t<T, 9>(ctx, a, grid);
+    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+}
+
+template <typename T>
+static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm, int64_t stride,
+                          int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
+    const int M = ctx->M, hdrB = header_bytes(ctx);
+    const bool pacDev = is_device_ptr(pac), pcmDev = is_device_ptr(pcm);
+    const int64_t total = pacOff[S] - pacOff[0];
+    const uint8_t *d_pac;
+    if (pacDev) d_pac = pac;
+    else {
+        CK(ctx->w_misc.ensure((size_t)total + 16));
+        CK(cudaMemcpyAsync(ctx->w_misc.p, pac + pacOff[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        d_pac = ctx->w_misc.as<uint8_t>() - pacOff[0];
+    }
+    // headers (pacfile.py:123-151): must describe this context's layout
+    std::vector<uint8_t> hdr((size_t)S * hdrB);
+    int64_t maxLen = 0;
+    for (int s = 0; s < S; s++) {
+        int64_t len = pacOff[s + 1] - pacOff[s];
+        if (len < hdrB) FAIL(PAC_E_FORMAT, "stream %d shorter than a PAC header", s);
+        if (len > maxLen) maxLen = len;
+        if (pacDev) CK(cudaMemcpyAsync(hdr.data() + (size_t)s * hdrB, pac + pacOff[s], hdrB, cudaMemcpyDeviceToHost, ctx->stream));
+        else memcpy(hdr.data() + (size_t)s * hdrB, pac + pacOff[s], hdrB);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    auto rd32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    auto rd16 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); };
+    for (int s = 0; s < S; s++) {
+        const uint8_t *h = hdr.data() + (size_t)s * hdrB;
+        if (memcmp(h, "PAC ", 4)) FAIL(PAC_E_FORMAT, "stream %d: Tried to read a non-PAC file into a PACFile object", s);   // pacfile.py:130
+        if ((int)rd16(h + 8) != 2 || (int)rd32(h + 14) != M || (int)rd16(h + 18) != ctx->p.nScaleBits ||
+            (int)rd16(h + 20) != ctx->p.nMantSizeBits || (int)rd32(h + 22) != ctx->bands.nBands)
+            FAIL(PAC_E_FORMAT, "stream %d: header does not match this context's coding parameters", s);
+        for (int b = 0; b < ctx->bands.nBands; b++)
+            if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s);
+        if (hdrSampleRate) hdrSampleRate[s] = (int32_t)rd32(h + 4);
+        if (hdrNumSamples) hdrNumSamples[s] = rd32(h + 10);
+    }
+    const int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
+    const int maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
+    if ((int64_t)(maxBlocks) * M > stride && stride < pac_decode_bound(ctx, maxLen)) {
+        // the caller may legitimately pass a tighter stride when it knows the block count; checked after indexing
+    }
+    // ---- index
+    CK(ctx->w_ns.ensure((size_t)(S + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->w_ns.p, pacOff, (size_t)(S + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t nblkAll = (int64_t)S * maxBlocks;
+    CK(ctx->w_coff.ensure((size_t)nblkAll * 2 * 8));
+    CK(ctx->w_nby.ensure((size_t)nblkAll * 2 * 4));
+    CK(ctx->w_misc2.ensure((size_t)S * 4));   // nBlocks
+    CK(ctx->w_misc3.ensure((size_t)S * 4));   // status
+    IndexArgs ia{};
+    ia.pac = d_pac; ia.pacOff = ctx->w_ns.as<int64_t>(); ia.S = S; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
+    ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
+    ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
+    k_index<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ia);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<int32_t> nblk(S), stt(S);
+    CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < S; s++) {
+        if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s);   // pacfile.py:184
+        if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s, (long long)nblk[s] * M);
+    }
+    // ---- unpack + dequantise
+    CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(T)));
+    CK(ctx->w_lrms.ensure((size_t)nblkAll * 4));
+    CK(cudaMemsetAsync(ctx->w_misc3.p, 0, (size_t)S * 4, ctx->stream));
+    UnpackArgs<T> ua{};
+    ua.pac = d_pac; ua.chunkPos = ia.chunkPos; ua.chunkLen = ia.chunkLen; ua.nBlocks = ia.nBlocks;
+    ua.S = S; ua.maxBlocks = maxBlocks; ua.M = M;
+    ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;   // pacfile.py:189
+    ua.lines = ctx->w_lines.as<T>(); ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
+    ua.dt = ctx->dt; ua.bands = ctx->bands;
+    {
+        int64_t nchunk = nblkAll * 2;
+        int64_t grid = (nchunk + 63) / 64;
+        if (grid > (int64_t)ctx->numSMs * 32) grid = (int64_t)ctx->numSMs * 32;
+        k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- synthesis
+    int16_t *d_pcm;
+    if (pcmDev) d_pcm = pcm;
+    else { CK(ctx->w_pcm.ensure((size_t)S * stride * 4)); d_pcm = ctx->w_pcm.as<int16_t>(); }
+    CK(ctx->w_misc4.ensure((size_t)S * 8));
+    SynthArgs<T> sa{};
+    sa.lines = ua.lines; sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = S; sa.maxBlocks = maxBlocks; sa.run = 16;
+    sa.pcm = d_pcm; sa.strideSamples = stride; sa.nSamplesOut = ctx->w_misc4.as<int64_t>(); sa.rawOut = nullptr;
+    int runsPerStream = (maxBlocks + sa.run) / sa.run;
+    int rc = launch_synth<T>(ctx, sa, (int64_t)S * runsPerStream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stt.data(), ctx->w_misc3.p, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < S; s++) {
+        if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: malformed chunk (bad table ID or code)", s);
+        nSamplesOut[s] = (int64_t)nblk[s] * M;
+    }
+    if (!pcmDev) {
+        int64_t maxS = 0;
+        for (int s = 0; s < S; s++) if (nSamplesOut[s] > maxS) maxS = nSamplesOut[s];
+        if (maxS > 0) CK(cudaMemcpy2D(pcm, (size_t)stride * 4, d_pcm, (size_t)stride * 4, (size_t)maxS * 4, (size_t)S, cudaMemcpyDeviceToHost));
+    }
+    return PAC_OK;
+}
+
+extern "C" int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,
+                                int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
+    if (!ctx) return PAC_E_ARG;
+    if (!pac || !pacOff || !pcm || !nSamplesOut || S <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_batch");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return decode_batch_t<double>(ctx, pac, pacOff, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+    return decode_batch_t<float>(ctx, pac, pacOff, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+}
+
+// ------------------------------------------------------------------ per-block API
+template <typename T>
+static int encode_blocks_t(PacCtx *ctx, const double *data, int nblk, PacStreamState *state, int32_t *scaleFactor, int32_t *bitAlloc,
+                           int32_t *mant, int32_t *tableID, int32_t *overallScale, int32_t *lrms, uint8_t *chunk, int64_t chunkCap,
+                           int32_t *chunkBytes) {
+    const int M = ctx->M, N = ctx->N, NB = ctx->bands.nBands;
+    const int64_t nwork = nblk;
+    CK(ctx->w_misc.ensure((size_t)nwork * 2 * N * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, data, (size_t)nwork * 2 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<StreamState> st(nblk);
+    for (int i = 0; i < nblk; i++) { st[i].extraBits = state[i].extraBits; st[i].bitDeposit = state[i].bitDeposit; st[i].outOffset = 0; st[i].reserved = 0; }
+    CK(ctx->w_state.ensure((size_t)nblk * sizeof(StreamState)));
+    CK(cudaMemcpyAsync(ctx->w_state.p, st.data(), (size_t)nblk * sizeof(StreamState), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->w_lines.ensure((size_t)nwork * 2 * M * sizeof(T)));
+    CK(ctx->w_smr.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+    CK(ctx->w_bmax.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+    CK(ctx->w_osc.ensure((size_t)nwork * 2));
+    CK(ctx->w_lrms.ensure((size_t)nwork * 4));
+    CK(ctx->w_ba.ensure((size_t)nwork * 2 * kMaxBands));
+    CK(ctx->w_sf.ensure((size_t)nwork * 2 * kMaxBands));
+    CK(ctx->w_tid.ensure((size_t)nwork * 2));
+    CK(ctx->w_nby.ensure((size_t)nwork * 2 * 4));
+    CK(ctx->w_coff.ensure((size_t)nwork * 2 * 8));
+    const int64_t ccap = 4096;
+    CK(ctx->w_out.ensure((size_t)nwork * 2 * ccap));
+    CK(ctx->w_misc2.ensure((size_t)nwork * 2 * M * 4));
+    CK(cudaMemsetAsync(ctx->w_misc2.p, 0, (size_t)nwork * 2 * M * 4, ctx->stream));
+    CK(ctx->w_ovf.ensure((size_t)nblk * 4));
+    CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)nblk * 4, ctx->stream));
+    AnalysisArgs<T> aa{};
+    aa.pcm = nullptr; aa.blocks = ctx->w_misc.as<double>(); aa.S = nblk; aa.b0 = 0; aa.nb = 1; aa.nwork = nwork;
+    aa.lines = ctx->w_lines.as<T>(); aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>();
+    aa.oscale = ctx->w_osc.as<uint8_t>(); aa.lrms = ctx->w_lrms.as<uint32_t>();
+    int rc = launch_analysis<T>(ctx, aa);
+    if (rc) return rc;
+    ScanArgs<T> sa{};
+    sa.S = nblk; sa.b0 = 0; sa.nb = 1; sa.nSamples = nullptr; sa.state = ctx->w_state.as<StreamState>();
+    sa.lines = aa.lines; sa.smr = aa.smr; sa.bmax = aa.bmax; sa.lrms = aa.lrms;
+    sa.ba = ctx->w_ba.as<uint8_t>(); sa.sf = ctx->w_sf.as<uint8_t>(); sa.tableID = ctx->w_tid.as<uint8_t>();
+    sa.nbytes = ctx->w_nby.as<uint32_t>(); sa.chunkOff = ctx->w_coff.as<long long>();
+    if ((rc = launch_scan<T>(ctx, sa))) return rc;
+    PackArgs<T> pa{};
+    pa.S = nblk; pa.b0 = 0; pa.nb = 1; pa.nSamples = nullptr;
+    pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
+    pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = ctx->w_out.as<uint8_t>(); pa.cap = ccap; pa.perChunk = 1;
+    pa.overflow = ctx->w_ovf.as<int>(); pa.o_mant = ctx->w_misc2.as<int32_t>(); pa.header = nullptr; pa.headerBytes = 0;
+    if ((rc = launch_pack<T>(ctx, pa))) return rc;
+    std::vector<uint8_t> hba((size_t)nwork * 2 * kMaxBands), hsf((size_t)nwork * 2 * kMaxBands), htid((size_t)nwork * 2), hosc((size_t)nwork * 2);
+    std::vector<uint32_t> hlr(nwork), hnby((size_t)nwork * 2);
+    CK(cudaMemcpyAsync(hba.data(), sa.ba, hba.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hsf.data(), sa.sf, hsf.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(htid.data(), sa.tableID, htid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hosc.data(), aa.oscale, hosc.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hlr.data(), aa.lrms, hlr.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hnby.data(), sa.nbytes, hnby.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(st.data(), ctx->w_state.p, (size_t)nblk * sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mant) CK(cudaMemcpyAsync(mant, ctx->w_misc2.p, (size_t)nwork * 2 * M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < nwork; w++) {
+        state[w].extraBits = st[w].extraBits; state[w].bitDeposit = st[w].bitDeposit;
+        if (lrms) lrms[w] = (int32_t)hlr[w];
+        for (int ch = 0; ch < 2; ch++) {
+            if (tableID) tableID[w * 2 + ch] = htid[w * 2 + ch];
+            if (overallScale) overallScale[w * 2 + ch] = hosc[w * 2 + ch];
+            if (chunkBytes) chunkBytes[w * 2 + ch] = (int32_t)hnby[w * 2 + ch];
+            for (int bd = 0; bd < NB; bd++) {
+                if (scaleFactor) scaleFactor[(w * 2 + ch) * NB + bd] = hsf[(w * 2 + ch) * kMaxBands + bd];
+                if (bitAlloc) bitAlloc[(w * 2 + ch) * NB + bd] = hba[(w * 2 + ch) * kMaxBands + bd];
+            }
+            if (chunk) {
+                if ((int64_t)hnby[w * 2 + ch] > chunkCap) FAIL(PAC_E_OVERFLOW, "chunkCap too small (%u needed)", hnby[w * 2 + ch]);
+                CK(cudaMemcpy(chunk + (w * 2 + ch) * chunkCap, ctx->w_out.as<uint8_t>() + (w * 2 + ch) * ccap, hnby[w * 2 + ch], cudaMemcpyDeviceToHost));
+            }
+        }
+    }
+    return PAC_OK;
+}
+
+extern "C" int pac_encode_blocks(PacCtx *ctx, const double *data, int nblk, PacStreamState *state, int32_t *scaleFactor,
+                                 int32_t *bitAlloc, int32_t *mant, int32_t *tableID, int32_t *overallScale, int32_t *lrms,
+                                 uint8_t *chunk, int64_t chunkCap, int32_t *chunkBytes) {
+    if (!ctx) return PAC_E_ARG;
+    if (!data || !state || nblk <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_encode_blocks");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64)
+        return encode_blocks_t<double>(ctx, data, nblk, state, scaleFactor, bitAlloc, mant, tableID, overallScale, lrms, chunk, chunkCap, chunkBytes);
+    return encode_blocks_t<float>(ctx, data, nblk, state, scaleFactor, bitAlloc, mant, tableID, overallScale, lrms, chunk, chunkCap, chunkBytes);
+}
+
+// dequantise kernel for the per-block decode API (codec.py:31-43)
+template <typename T>
+__global__ void k_dequant_blocks(const int32_t *sf, const int32_t *ba, const int32_t *mant, const int32_t *oscale, int nblk, int M,
+                                 int nScaleBits, T *lines, BandInfo bands) {
+    const int NB = bands.nBands;
+    int64_t total = (int64_t)nblk * 2 * M;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = e / M;
+        int i = (int)(e - c * M);
+        int bd = 0;
+        while (bd < NB - 1 && i >= bands.lo[bd + 1]) bd++;
+        int b = ba[c * NB + bd];
+        double v = 0.0;
+        if (b) v = dequant(sf[c * NB + bd], (long long)mant[e], (1 << nScaleBits) - 1, b) / (double)(1 << oscale[c]);
+        lines[e] = (T)v;
+    }
+}
+
+template <typename T>
+static int decode_blocks_t(PacCtx *ctx, const int32_t *scaleFactor, const int32_t *bitAlloc, const int32_t *mant,
+                           const int32_t *overallScale, const int32_t *lrms, int nblk, double *out) {
+    const int M = ctx->M, N = ctx->N, NB = ctx->bands.nBands;
+    CK(ctx->w_misc.ensure((size_t)nblk * 2 * NB * 4));
+    CK(ctx->w_misc2.ensure((size_t)nblk * 2 * NB * 4));
+    CK(ctx->w_misc3.ensure((size_t)nblk * 2 * M * 4));
+    CK(ctx->w_misc4.ensure((size_t)nblk * 2 * 4));
+    CK(ctx->w_lrms.ensure((size_t)nblk * 4));
+    CK(ctx->w_lines.ensure((size_t)nblk * 2 * M * sizeof(T)));
+    CK(ctx->w_misc5.ensure((size_t)nblk * 2 * N * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, scaleFactor, (size_t)nblk * 2 * NB * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc2.p, bitAlloc, (size_t)nblk * 2 * NB * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc3.p, mant, (size_t)nblk * 2 * M * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc4.p, overallScale, (size_t)nblk * 2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_lrms.p, lrms, (size_t)nblk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_dequant_blocks<T><<<(unsigned)((nblk * 2 * M + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->w_misc.as<int32_t>(), ctx->w_misc2.as<int32_t>(), ctx->w_misc3.as<int32_t>(), ctx->w_misc4.as<int32_t>(), nblk, M,
+        ctx->p.nScaleBits, ctx->w_lines.as<T>(), ctx->bands);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    SynthArgs<T> sa{};
+    sa.lines = ctx->w_lines.as<T>(); sa.lrms = ctx->w_lrms.as<uint32_t>(); sa.nBlocks = nullptr; sa.S = 1; sa.maxBlocks = nblk; sa.run = 1;
+    sa.pcm = nullptr; sa.strideSamples = 0; sa.nSamplesOut = nullptr; sa.rawOut = ctx->w_misc5.as<double>();
+    int rc = launch_synth<T>(ctx, sa, nblk);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->w_misc5.p, (size_t)nblk * 2 * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PAC_OK;
+}
+
+extern "C" int pac_decode_blocks(PacCtx *ctx, const int32_t *scaleFactor, const int32_t *bitAlloc, const int32_t *mant,
+                                 const int32_t *overallScale, const int32_t *lrms, int nblk, double *out) {
+    if (!ctx) return PAC_E_ARG;
+    if (!scaleFactor || !bitAlloc || !mant || !overallScale || !lrms || !out || nblk <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_blocks");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return decode_blocks_t<double>(ctx, scaleFactor, bitAlloc, mant, overallScale, lrms, nblk, out);
+    return decode_blocks_t<float>(ctx, scaleFactor, bitAlloc, mant, overallScale, lrms, nblk, out);
+}
+
+extern "C" int pac_unpack_blocks(PacCtx *ctx, const uint8_t *chunks, int64_t chunkCap, const int32_t *chunkBytes, int nblk,
+                                 int32_t *scaleFactor, int32_t *bitAlloc, int32_t *mant, int32_t *overallScale, int32_t *lrms,
+                                 int32_t *tableID) {
+    if (!ctx) return PAC_E_ARG;
+    if (!chunks || !chunkBytes || nblk <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_unpack_blocks");
+    CK(cudaSetDevice(ctx->device));
+    const int M = ctx->M, NB = ctx->bands.nBands;
+    const int64_t nchunk = (int64_t)nblk * 2;
+    CK(ctx->w_misc.ensure((size_t)nchunk * chunkCap + 16));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, chunks, (size_t)nchunk * chunkCap, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int64_t> pos(nchunk);
+    for (int64_t c = 0; c < nchunk; c++) pos[c] = c * chunkCap;
+    CK(ctx->w_coff.ensure((size_t)nchunk * 8));
+    CK(cudaMemcpyAsync(ctx->w_coff.p, pos.data(), (size_t)nchunk * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->w_nby.ensure((size_t)nchunk * 4));
+    CK(cudaMemcpyAsync(ctx->w_nby.p, chunkBytes, (size_t)nchunk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->w_lrms.ensure((size_t)nblk * 4));
+    CK(ctx->w_misc2.ensure((size_t)nchunk * kMaxBands * 4));
+    CK(ctx->w_misc3.ensure((size_t)nchunk * kMaxBands * 4));
+    CK(ctx->w_misc4.ensure((size_t)nchunk * M * 4));
+    CK(ctx->w_misc5.ensure((size_t)nchunk * 4));
+    CK(ctx->w_misc6.ensure((size_t)nchunk * 4));
+    CK(ctx->w_ovf.ensure(4));
+    CK(cudaMemsetAsync(ctx->w_ovf.p, 0, 4, ctx->stream));
+    UnpackArgs<double> ua{};
+    ua.pac = ctx->w_misc.as<uint8_t>(); ua.chunkPos = ctx->w_coff.as<int64_t>(); ua.chunkLen = ctx->w_nby.as<int32_t>(); ua.nBlocks = nullptr;
+    ua.S = 1; ua.maxBlocks = nblk; ua.M = M;
+    ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;
+    ua.lines = nullptr; ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_ovf.as<int32_t>();
+    ua.o_sf = ctx->w_misc2.as<int32_t>(); ua.o_ba = ctx->w_misc3.as<int32_t>(); ua.o_mant = ctx->w_misc4.as<int32_t>();
+    ua.o_oscale = ctx->w_misc5.as<int32_t>(); ua.o_tableID = ctx->w_misc6.as<int32_t>();
+    ua.dt = ctx->dt; ua.bands = ctx->bands;
+    k_unpack<double><<<(unsigned)((nchunk + 63) / 64), 64, 0, ctx->stream>>>(ua);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<int32_t> hsf((size_t)nchunk * kMaxBands), hba((size_t)nchunk * kMaxBands);
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(hsf.data(), ua.o_sf, hsf.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hba.data(), ua.o_ba, hba.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mant) CK(cudaMemcpyAsync(mant, ua.o_mant, (size_t)nchunk * M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (overallScale) CK(cudaMemcpyAsync(overallScale, ua.o_oscale, (size_t)nchunk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tableID) CK(cudaMemcpyAsync(tableID, ua.o_tableID, (size_t)nchunk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lrms) CK(cudaMemcpyAsync(lrms, ua.lrms, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&err, ua.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t c = 0; c < nchunk; c++)
+        for (int bd = 0; bd < NB; bd++) {
+            if (scaleFactor) scaleFactor[c * NB + bd] = hsf[c * kMaxBands + bd];
+            if (bitAlloc) bitAlloc[c * NB + bd] = hba[c * kMaxBands + bd];
+        }
+    if (err) FAIL(PAC_E_FORMAT, "malformed chunk (bad table ID or code)");
+    return PAC_OK;
+}
+
+// ------------------------------------------------------------------ L2 entry points
+static int get_window(PacCtx *ctx, int kind, int N, const double **dptr) {
+    int key = kind * 65536 + ilog2(N);
+    auto it = ctx->winTables.find(key);
+    if (it == ctx->winTables.end()) {
+        std::vector<double> w(N);
+        double Nf = (double)N;
+        if (kind == 0) for (int n = 0; n < N; n++) w[n] = sin((n + 0.5) * M_PI / Nf);                        // window.py:35-37
+        else if (kind == 1) for (int n = 0; n < N; n++) w[n] = 0.5 * (1 - cos(2.0 * (n + 0.5) * M_PI / Nf)); // window.py:49-51
+        else {                                                                                              // window.py:56-78, alpha = 4
+            auto i0 = [](double x) { double s = 1, t = 1, q = x * x / 4; for (int k = 1; k < 500; k++) { t *= q / ((double)k * k); s += t; if (t < s * 1e-18) break; } return s; };
+            int half = N / 2;
+            std::vector<double> kz(half + 1);
+            double den = 0, d0 = i0(M_PI * 4.0);
+            for (int t = 0; t <= half; t++) { double u = 4.0 * t / Nf - 1.0, a = 1.0 - u * u; if (a < 0) a = 0; kz[t] = i0(4.0 * M_PI * sqrt(a)) / d0; den += kz[t] * kz[t]; }
+            double c = 0;
+            for (int t = 0; t < half; t++) { c += kz[t] * kz[t]; w[t] = w[N - 1 - t] = sqrt(c / den); }
+        }
+        void *d = nullptr;
+        CK(cudaMalloc(&d, (size_t)N * 8));
+        CK(cudaMemcpy(d, w.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+        it = ctx->winTables.emplace(key, d).first;
+    }
+    *dptr = reinterpret_cast<const double *>(it->second);
+    return PAC_OK;
+}
+
+extern "C" int pac_window(PacCtx *ctx, int kind, double *x, int n, int N) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || n <= 0 || N <= 0 || kind < 0 || kind > 2 || (kind == 2 && (N & 1))) FAIL(PAC_E_ARG, "bad arguments to pac_window");
+    CK(cudaSetDevice(ctx->device));
+    const double *w;
+    int rc = get_window(ctx, kind, N, &w);
+    if (rc) return rc;
+    int64_t total = (int64_t)n * N;
+    CK(ctx->w_misc.ensure((size_t)total * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, x, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t grid = (total + 255) / 256;
+    if (grid > 65535) grid = 65535;
+    k_window<<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->w_misc.as<double>(), w, total, N);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x, ctx->w_misc.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PAC_OK;
+}
+
+template <typename T, int LOGM>
+static int mdct_run(PacCtx *ctx, bool inverse, const double *in, int n, double *out) {
+    constexpr int M = 1 << LOGM, N = 2 * M, NT = (M / 4 > 0 ? M / 4 : 1);
+    DevTables<T> tb;
+    int rc = get_tables<T>(ctx, N, &tb);
+    if (rc) return rc;
+    size_t nin = (size_t)n * (inverse ? M : N) * 8, nout = (size_t)n * (inverse ? N : M) * 8;
+    CK(ctx->w_misc.ensure(nin));
+    CK(ctx->w_misc2.ensure(nout));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, in, nin, cudaMemcpyHostToDevice, ctx->stream));
+    size_t smem = sizeof(MdctSmem<T, LOGM>);
+    if (inverse) {
+        CK(cudaFuncSetAttribute(k_imdct<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_imdct<T, LOGM><<<n, NT, smem, ctx->stream>>>(ctx->w_misc.as<double>(), ctx->w_misc2.as<double>(), n, tb);
+    } else {
+        CK(cudaFuncSetAttribute(k_mdct<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mdct<T, LOGM><<<n, NT, smem, ctx->stream>>>(ctx->w_misc.as<double>(), ctx->w_misc2.as<double>(), n, tb);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->w_misc2.p, nout, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PAC_OK;
+}
+
+template <typename T>
+static int mdct_dispatch(PacCtx *ctx, bool inverse, const double *in, int n, int N, double *out) {
+    switch (N) {
+        case 8: return mdct_run<T, 2>(ctx, inverse, in, n, out);
+        case 16: return mdct_run<T, 3>(ctx, inverse, in, n, out);
+        case 256: return mdct_run<T, 7>(ctx, inverse, in, n, out);
+        case 512: return mdct_run<T, 8>(ctx, inverse, in, n, out);
+        case 1024: return mdct_run<T, 9>(ctx, inverse, in, n, out);
+        case 2048: return mdct_run<T, 10>(ctx, inverse, in, n, out);
+        case 4096: return mdct_run<T, 11>(ctx, inverse, in, n, out);
+    }
+    FAIL(PAC_E_ARG, "MDCT block length %d not supported (8, 16, 256, 512, 1024, 2048, 4096)", N);
+}
+
+extern "C" int pac_mdct(PacCtx *ctx, const double *x, int n, int N, double *X) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !X || n <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_mdct");
+    CK(cudaSetDevice(ctx->device));
+    return ctx->precision == PAC_PRECISION_FP64 ? mdct_dispatch<double>(ctx, false, x, n, N, X) : mdct_dispatch<float>(ctx, false, x, n, N, X);
+}
+
+extern "C" int pac_imdct(PacCtx *ctx, const double *X, int n, int N, double *x) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !X || n <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_imdct");
+    CK(cudaSetDevice(ctx->device));
+    return ctx->precision == PAC_PRECISION_FP64 ? mdct_dispatch<double>(ctx, true, X, n, N, x) : mdct_dispatch<float>(ctx, true, X, n, N, x);
+}
+
+template <typename T>
+static int analysis_t(PacCtx *ctx, const double *data, int nblk, int32_t *lrms, int32_t *oscale, double *mdct, double *bthr,
+                      double *smr, double *lines) {
+    const int M = ctx->M, N = ctx->N, NB = ctx->bands.nBands;
+    const int64_t nwork = nblk;
+    CK(ctx->w_misc.ensure((size_t)nwork * 2 * N * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, data, (size_t)nwork * 2 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->w_lines.ensure((size_t)nwork * 2 * M * sizeof(T)));
+    CK(ctx->w_smr.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+    CK(ctx->w_bmax.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
+    CK(ctx->w_osc.ensure((size_t)nwork * 2));
+    CK(ctx->w_lrms.ensure((size_t)nwork * 4));
+    CK(ctx->w_dbg1.ensure((size_t)nwork * 2 * M * sizeof(T)));
+    CK(ctx->w_dbg2.ensure((size_t)nwork * 6 * M * sizeof(T)));
+    AnalysisArgs<T> aa{};
+    aa.pcm = nullptr; aa.blocks = ctx->w_misc.as<double>(); aa.S = nblk; aa.b0 = 0; aa.nb = 1; aa.nwork = nwork;
+    aa.lines = ctx->w_lines.as<T>(); aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>();
+    aa.oscale = ctx->w_osc.as<uint8_t>(); aa.lrms = ctx->w_lrms.as<uint32_t>();
+    aa.dbg_mdct = ctx->w_dbg1.as<T>(); aa.dbg_bthr = ctx->w_dbg2.as<T>();
+    int rc = launch_analysis<T>(ctx, aa);
+    if (rc) return rc;
+    std::vector<T> hl((size_t)nwork * 2 * M), hm((size_t)nwork * 2 * M), hb((size_t)nwork * 6 * M), hs((size_t)nwork * 2 * kMaxBands);
+    std::vector<uint8_t> hosc((size_t)nwork * 2);
+    std::vector<uint32_t> hlr(nwork);
+    CK(cudaMemcpyAsync(hl.data(), aa.lines, hl.size() * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hm.data(), aa.dbg_mdct, hm.size() * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hb.data(), aa.dbg_bthr, hb.size() * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs.data(), aa.smr, hs.size() * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hosc.data(), aa.oscale, hosc.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hlr.data(), aa.lrms, hlr.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < nwork; w++) {
+        if (lrms) lrms[w] = (int32_t)hlr[w];
+        for (int ch = 0; ch < 2; ch++) {
+            if (oscale) oscale[w * 2 + ch] = hosc[w * 2 + ch];
+            if (smr) for (int bd = 0; bd < NB; bd++) smr[(w * 2 + ch) * NB + bd] = (double)hs[(w * 2 + ch) * kMaxBands + bd];
+        }
+    }
+    if (lines) for (size_t i = 0; i < hl.size(); i++) lines[i] = (double)hl[i];
+    if (mdct) for (size_t i = 0; i < hm.size(); i++) mdct[i] = (double)hm[i];
+    if (bthr) for (size_t i = 0; i < hb.size(); i++) bthr[i] = (double)hb[i];
+    return PAC_OK;
+}
+
+extern "C" int pac_analysis(PacCtx *ctx, const double *data, int nblk, int32_t *lrms, int32_t *oscale, double *mdct, double *bthr,
+                            double *smr, double *lines) {
+    if (!ctx) return PAC_E_ARG;
+    if (!data || nblk <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_analysis");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return analysis_t<double>(ctx, data, nblk, lrms, oscale, mdct, bthr, smr, lines);
+    return analysis_t<float>(ctx, data, nblk, lrms, oscale, mdct, bthr, smr, lines);
+}
+
+template <typename T, int LOGM>
+static int calc_smrs_t(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr) {
+    constexpr int M = 1 << LOGM, N = 2 * M;
+    const int NB = ctx->bands.nBands;
+    CK(ctx->w_misc.ensure((size_t)n * N * 8));
+    CK(ctx->w_misc2.ensure((size_t)n * M * 8));
+    CK(ctx->w_misc3.ensure((size_t)n * kMaxBands * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, data, (size_t)n * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc2.p, mdct, (size_t)n * M * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SmrMonoArgs<T> a{};
+    a.data = ctx->w_misc.as<double>(); a.mdct = ctx->w_misc2.as<double>(); a.n = n; a.scale = scale;
+    a.smr = ctx->w_misc3.as<double>(); a.thr = nullptr; a.bands = ctx->bands;
+    int rc = get_tables<T>(ctx, N, &a.tab);
+    if (rc) return rc;
+    size_t smem = sizeof(AnalysisSmem<T, LOGM>);
+    CK(cudaFuncSetAttribute(k_calc_smrs<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_calc_smrs<T, LOGM><<<n, M / 4, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<double> hs((size_t)n * kMaxBands);
+    CK(cudaMemcpyAsync(hs.data(), a.smr, hs.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) for (int bd = 0; bd < NB; bd++) smr[(size_t)i * NB + bd] = hs[(size_t)i * kMaxBands + bd];
+    return PAC_OK;
+}
+
+extern "C" int pac_calc_smrs(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr) {
+    if (!ctx) return PAC_E_ARG;
+    if (!data || !mdct || !smr || n <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_calc_smrs");
+    CK(cudaSetDevice(ctx->device));
+    const bool f64 = ctx->precision == PAC_PRECISION_FP64;
+    if (ctx->LOGM == 10) return f64 ? calc_smrs_t<double, 10>(ctx, data, mdct, n, scale, smr) : calc_smrs_t<float, 10>(ctx, data, mdct, n, scale, smr);
+    if (ctx->LOGM == 9) return f64 ? calc_smrs_t<double, 9>(ctx, data, mdct, n, scale, smr) : calc_smrs_t<float, 9>(ctx, data, mdct, n, scale, smr);
+    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+}
+
+extern "C" int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *extraBits, int maxMantBits,
+                            const double *smr, const int32_t *lrms, int32_t *bits, int64_t *bitDifference) {
+    if (!ctx) return PAC_E_ARG;
+    if (n <= 0 || !bitBudget || !extraBits || !smr || !lrms || !bits || !bitDifference) FAIL(PAC_E_ARG, "bad arguments to pac_bitalloc");
+    CK(cudaSetDevice(ctx->device));
+    const int NB = ctx->bands.nBands;
+    CK(ctx->w_misc.ensure((size_t)n * 8)); CK(ctx->w_misc2.ensure((size_t)n * 8)); CK(ctx->w_misc3.ensure((size_t)n * NB * 8));
+    CK(ctx->w_misc4.ensure((size_t)n * 4)); CK(ctx->w_misc5.ensure((size_t)n * NB * 4)); CK(ctx->w_misc6.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, bitBudget, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc2.p, extraBits, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc3.p, smr, (size_t)n * NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_misc4.p, lrms, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_bitalloc<<<(n + 3) / 4, 128, 0, ctx->stream>>>(n, ctx->w_misc.as<double>(), ctx->w_misc2.as<long long>(), maxMantBits,
+                                                     ctx->w_misc3.as<double>(), ctx->w_misc4.as<uint32_t>(), ctx->w_misc5.as<int32_t>(),
+                                                     ctx->w_misc6.as<long long>(), ctx->bands);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bits, ctx->w_misc5.p, (size_t)n * NB * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(bitDifference, ctx->w_misc6.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PAC_OK;
+}
+
+// small helper for the element-wise quantiser entry points
+#define ELEMWISE(IN_T, OUT_T, inptr, outptr, n, launch)                                                        \
+    do {                                                                                                      \
+        CK(cudaSetDevice(ctx->device));                                                                       \
+        CK(ctx->w_misc.ensure((size_t)(n) * sizeof(IN_T)));                                                   \
+        CK(ctx->w_misc2.ensure((size_t)(n) * sizeof(OUT_T)));                                                 \
+        CK(cudaMemcpyAsync(ctx->w_misc.p, inptr, (size_t)(n) * sizeof(IN_T), cudaMemcpyHostToDevice, ctx->stream)); \
+        launch;                                                                                               \
+        ctx->launches++;                                                                                      \
+        CK(cudaGetLastError());                                                                               \
+        CK(cudaMemcpyAsync(outptr, ctx->w_misc2.p, (size_t)(n) * sizeof(OUT_T), cudaMemcpyDeviceToHost, ctx->stream)); \
+        CK(cudaStreamSynchronize(ctx->stream));                                                               \
+    } while (0)
+
+extern "C" int pac_scale_factor(PacCtx *ctx, const double *x, int n, int nScaleBits, int nMantBits, int32_t *scale) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !scale || n <= 0 || nScaleBits > 5 || nMantBits > 32) FAIL(PAC_E_ARG, "bad arguments to pac_scale_factor");
+    ELEMWISE(double, int32_t, x, scale, n, (k_scale_factor<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->w_misc.as<double>(), n, nScaleBits, nMantBits, ctx->w_misc2.as<int32_t>())));
+    return PAC_OK;
+}
+extern "C" int pac_vquantize_uniform(PacCtx *ctx, const double *x, int n, int nBits, uint64_t *q) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !q || n <= 0 || nBits < 1 || nBits > 52) FAIL(PAC_E_ARG, "bad arguments to pac_vquantize_uniform");
+    ELEMWISE(double, uint64_t, x, q, n, (k_vquantize_uniform<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->w_misc.as<double>(), n, nBits, ctx->w_misc2.as<unsigned long long>())));
+    return PAC_OK;
+}
+extern "C" int pac_vdequantize_uniform(PacCtx *ctx, const uint64_t *q, int n, int nBits, double *x) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !q || n <= 0 || nBits < 1 || nBits > 52) FAIL(PAC_E_ARG, "bad arguments to pac_vdequantize_uniform");
+    ELEMWISE(uint64_t, double, q, x, n, (k_vdequantize_uniform<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->w_misc.as<unsigned long long>(), n, nBits, ctx->w_misc2.as<double>())));
+    return PAC_OK;
+}
+extern "C" int pac_vmantissa(PacCtx *ctx, const double *x, int n, int scale, int nScaleBits, int nMantBits, uint64_t *m) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !m || n <= 0 || nScaleBits > 5 || nMantBits < 1 || nMantBits > 32) FAIL(PAC_E_ARG, "bad arguments to pac_vmantissa");
+    ELEMWISE(double, uint64_t, x, m, n, (k_vmantissa<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->w_misc.as<double>(), n, scale, nScaleBits, nMantBits, ctx->w_misc2.as<unsigned long long>())));
+    return PAC_OK;
+}
+extern "C" int pac_vdequantize(PacCtx *ctx, int scale, const int64_t *m, int n, int nScaleBits, int nMantBits, double *x) {
+    if (!ctx) return PAC_E_ARG;
+    if (!x || !m || n <= 0 || nScaleBits > 5 || nMantBits < 1 || nMantBits > 32) FAIL(PAC_E_ARG, "bad arguments to pac_vdequantize");
+    ELEMWISE(int64_t, double, m, x, n, (k_vdequantize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(scale, ctx->w_misc.as<long long>(), n, nScaleBits, nMantBits, ctx->w_misc2.as<double>())));
+    return PAC_OK;
+}

@@ -1,0 +1,132 @@
+// stages.cuh -- kernels behind the reference's L2 function names (window.py, mdct.py, quantize.py, bitalloc.py)
+// when they are called one stage at a time through the Python shim.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include "scan.cuh"
+
+namespace pac {
+
+// window.py:27-53,56-78.  w[n] precomputed on the host (sine / hann / kbd), x [n][N] in place.
+__global__ void k_window(double *x, const double *w, int64_t total, int N) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] *= w[i % N];
+}
+
+template <typename T, int LOGM>
+struct MdctSmem {
+    static constexpr int M = 1 << LOGM;
+    using T2 = typename Vec2<T>::type;
+    T x[2 * M];
+    T2 W[M / 2 + 2];
+};
+
+// mdct.py:49-71: MDCT(data, M, M) by fold + M/2-point complex FFT (tests/model_analysis.py:mdct_fold_fft)
+template <typename T, int LOGM>
+__global__ void k_mdct(const double *in, double *out, int n, DevTables<T> tb) {
+    using SS = MdctSmem<T, LOGM>;
+    using T2 = typename Vec2<T>::type;
+    constexpr int M = SS::M, N = 2 * M, H = M / 2, NT = (M / 4 > 0 ? M / 4 : 1);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SS &sm = *reinterpret_cast<SS *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t w = blockIdx.x;
+    for (int i = tid; i < N; i += NT) sm.x[i] = (T)in[w * N + i];
+    __syncthreads();
+    for (int k = tid; k < H; k += NT) {
+        const T *x = sm.x;
+        int m0 = 2 * k, m1 = M - 1 - 2 * k;
+        T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
+        T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
+        sm.W[k] = cmul(mk2<T>(u0, u1), tb.mdct_pre[k]);
+    }
+    __syncthreads();
+    fft_dif<T, LOGM - 1, NT>(sm.W, 1, H + 2, tb.tw, 2);
+    for (int k = tid; k < H; k += NT) {
+        T2 y = cmul(sm.W[fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+        out[w * M + 2 * k] = (double)(((T)2 / (T)N) * y.x);
+        out[w * M + M - 1 - 2 * k] = (double)(-((T)2 / (T)N) * y.y);
+    }
+}
+
+// mdct.py:73-88: IMDCT(data, M, M) = unfolded DCT-IV
+template <typename T, int LOGM>
+__global__ void k_imdct(const double *in, double *out, int n, DevTables<T> tb) {
+    using SS = MdctSmem<T, LOGM>;
+    using T2 = typename Vec2<T>::type;
+    constexpr int M = SS::M, N = 2 * M, H = M / 2, NT = (M / 4 > 0 ? M / 4 : 1);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SS &sm = *reinterpret_cast<SS *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t w = blockIdx.x;
+    for (int i = tid; i < M; i += NT) sm.x[i] = (T)in[w * M + i];
+    __syncthreads();
+    for (int k = tid; k < H; k += NT) sm.W[k] = cmul(mk2<T>(sm.x[2 * k], sm.x[M - 1 - 2 * k]), tb.mdct_pre[k]);
+    __syncthreads();
+    fft_dif<T, LOGM - 1, NT>(sm.W, 1, H + 2, tb.tw, 2);
+    for (int k = tid; k < H; k += NT) {
+        T2 y = cmul(sm.W[fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+        sm.x[2 * k] = y.x;
+        sm.x[M - 1 - 2 * k] = -y.y;
+    }
+    __syncthreads();
+    for (int nn = tid; nn < N; nn += NT) {
+        T v = nn < H ? sm.x[nn + H] : (nn < 3 * H ? -sm.x[3 * H - 1 - nn] : -sm.x[nn - 3 * H]);
+        out[w * N + nn] = (double)((T)2 * v);
+    }
+}
+
+// bitalloc.py:129-184, one warp per problem
+__global__ void k_bitalloc(int n, const double *bitBudget, const long long *extraBits, int maxMantBits, const double *smr,
+                           const uint32_t *lrms, int32_t *bits, long long *diff, BandInfo bands) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const int NB = bands.nBands;
+    double s = lane < NB ? smr[(int64_t)p * NB + lane] : 0.0;
+    long long d;
+    int b = warp_bitalloc(bitBudget[p], extraBits[p], maxMantBits, NB, 0, s, lrms[p], bands, &d);
+    if (lane < NB) bits[(int64_t)p * NB + lane] = b;
+    if (lane == 0) diff[p] = d;
+}
+
+// quantize.py
+__global__ void k_scale_factor(const double *x, int n, int nScaleBits, int nMantBits, int32_t *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = scale_factor(x[i], nScaleBits, nMantBits);
+}
+__global__ void k_vquantize_uniform(const double *x, int n, int nBits, unsigned long long *q) {   // :91-117
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long v = quant_mag(fabs(x[i]), nBits);
+    if (signbit(x[i])) v += 1ull << (nBits - 1);
+    q[i] = v;
+}
+__global__ void k_vdequantize_uniform(const unsigned long long *q, int n, int nBits, double *x) {   // :120-145
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long mask = 1ull << (nBits - 1), v = q[i];
+    bool neg = (v & mask) == mask;
+    if (neg) v -= mask;
+    double a = 2.0 * (double)v / ((double)(mask << 1) - 1.0);
+    x[i] = neg ? -a : a;
+}
+__global__ void k_vmantissa(const double *x, int n, int scale, int nScaleBits, int nMantBits, unsigned long long *m) {   // :315-342
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (nScaleBits < 0) nScaleBits = 0;
+    int largestScale = (1 << nScaleBits) - 1;
+    int R = nMantBits + largestScale;
+    unsigned long long q = quant_mag(fabs(x[i]), R);
+    unsigned long long v = (q << (scale + 1)) >> (R - nMantBits + 1);
+    if (signbit(x[i])) v += 1ull << (nMantBits - 1);
+    m[i] = v;
+}
+__global__ void k_vdequantize(int scale, const long long *m, int n, int nScaleBits, int nMantBits, double *x) {   // :345-376
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (nScaleBits < 0) nScaleBits = 0;
+    x[i] = dequant(scale, m[i], (1 << nScaleBits) - 1, nMantBits);
+}
+
+}  // namespace pac

@@ -1,0 +1,38 @@
+"""The restructured analysis algebra (tests/model_analysis.py == what csrc/analysis.cuh computes) reproduces the
+reference's own per-stage dumps.  CPU only."""
+import numpy as np
+
+import model_analysis as ma
+
+NL44 = [5, 4, 5, 5, 5, 5, 7, 7, 7, 9, 10, 11, 13, 15, 17, 21, 26, 32, 42, 51, 61, 83, 116, 163, 304]
+
+
+def test_pieces_against_numpy():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(2048)
+    np.testing.assert_allclose(ma.rfft_packed(x), np.fft.fft(x)[:1025], rtol=0, atol=2e-12)
+    n = np.arange(2048)
+    h = 0.5 * (1 - np.cos(2.0 * (n + 0.5) * np.pi / 2048))
+    F = np.fft.fft(x)[:1025]
+    np.testing.assert_allclose(ma.hann_taps(F, 2048), np.fft.fft(h * x)[:1025], rtol=0, atol=2e-12)
+    np.testing.assert_allclose(ma.hann_taps(ma.hann_taps(F, 2048), 2048), np.fft.fft(h * h * x)[:1025], rtol=0, atol=2e-12)
+    k = np.arange(1024)
+    ref = (2. / 2048) * np.real(np.fft.fft(x * np.exp(-1j * np.pi * n / 2048))[:1024]
+                                * np.exp(1j * (-2. * np.pi / 2048) * 512.5 * (k + 0.5)))
+    np.testing.assert_allclose(ma.mdct_fold_fft(x), ref, rtol=0, atol=1e-13)
+
+
+def test_model_matches_reference_stage_dumps(stages):
+    T = ma.Tables()
+    for key in [str(k) for k in stages["index"]]:
+        pcm = stages[key + ".pcm"].astype(np.float64)
+        x = np.sign(pcm) * 2.0 * np.abs(pcm) / 65535.0
+        lrms, osc, X, bthr, smr, lines = ma.analysis(T, x[:, 0].copy(), x[:, 1].copy(), NL44)
+        assert list(lrms) == list(stages[key + ".lrms"]), key
+        assert list(osc) == list(stages[key + ".oscale"]), key
+        ref = stages[key + ".mdct"]
+        assert np.max(np.abs(X - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1e-300), key
+        np.testing.assert_allclose(bthr, stages[key + ".bthr"], rtol=0, atol=1e-8, err_msg=key)
+        np.testing.assert_allclose(smr, stages[key + ".smr"], rtol=0, atol=1e-8, err_msg=key)
+        rl = stages[key + ".lines"]
+        assert np.max(np.abs(lines - rl)) <= 1e-12 * max(np.max(np.abs(rl)), 1e-300), key
