@@ -87,6 +87,18 @@ int  pac_band_layout(PacCtx *ctx, int32_t *nLines /*[PAC_MAX_BANDS]*/, int32_t *
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pac_launch_count(PacCtx *ctx);
 
+/* per-kernel device time, measured with CUDA events on the stream the kernels are launched on (bench.py's roofline).
+ * kinds index ms[] / count[]; timing adds two event records per launch and is off by default. */
+#define PAC_K_ANALYSIS 0   /* window + MDCT + M/S decision + SMR (analysis.cuh) */
+#define PAC_K_SCAN     1   /* reservoir scan: BitAlloc, scale factors, Huffman table search (scan.cuh) */
+#define PAC_K_PACK     2   /* quantise + Huffman code + bit pack (pack.cuh) */
+#define PAC_K_INDEX    3   /* decoder: chunk chain walk */
+#define PAC_K_UNPACK   4   /* decoder: bit unpack + Huffman decode + dequantise */
+#define PAC_K_SYNTH    5   /* decoder: M/S recombine + IMDCT + window + overlap-add + PCM */
+#define PAC_NKINDS     8
+int pac_timing_enable(PacCtx *ctx, int on);                       /* also resets the accumulators */
+int pac_timing_get(PacCtx *ctx, double *ms /*[PAC_NKINDS]*/, int64_t *count /*[PAC_NKINDS]*/);
+
 /* ------------------------------------------------------------------ whole streams (the hot path) */
 /* ceil(n/nMDCTLines)+1: pcmfile.py:66-82 + the flush block of pacfile.py:355-365 */
 int64_t pac_num_blocks(PacCtx *ctx, int64_t nSamples);
@@ -160,6 +172,12 @@ int pac_analysis(PacCtx *ctx, const double *data, int nblk, int32_t *lrms, int32
 /* psychoac.CalcSMRs (psychoac.py:253-318), mono: data [n][N] time samples (window NOT yet applied; the reference
  * applies Hann itself), mdct [n][N/2] lines scaled by 2^scale, -> smr [n][nBands] */
 int pac_calc_smrs(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr);
+/* psychoac.getMaskedThreshold (psychoac.py:215-251) / calcBTHR (:409-456) on n mono blocks: data [n][N] (the kernel
+ * applies the Hann window, :225/:428), noDrop as calcBTHR's flag -> thr [n][N/2] in dB */
+int pac_masked_threshold(PacCtx *ctx, const double *data, int n, int noDrop, double *thr);
+/* Huffman.encodeData's table search (Huffman.py:284-308) on n caller-supplied unsigned mantissas with their per-symbol
+ * bit allocation: tableID (1..10) and the total code bits under each table, totals [PAC_NTABLES] */
+int pac_huffman_select(PacCtx *ctx, const uint32_t *mag, const int32_t *ba, int n, int32_t *tableID, int64_t *totals);
 /* bitalloc.BitAlloc (bitalloc.py:129-184) on n independent problems */
 int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *extraBits, int maxMantBits,
                  const double *smr /*[n][nBands]*/, const int32_t *lrms /*[n] masks*/, int32_t *bits /*[n][nBands]*/,

@@ -73,6 +73,8 @@ def lib():
     L.pac_band_layout.argtypes = [vp, i32p, i32p]
     L.pac_launch_count.argtypes = [vp]
     L.pac_launch_count.restype = C.c_int64
+    L.pac_timing_enable.argtypes = [vp, C.c_int]
+    L.pac_timing_get.argtypes = [vp, dp, i64p]
     L.pac_num_blocks.argtypes = [vp, C.c_int64]
     L.pac_num_blocks.restype = C.c_int64
     L.pac_encode_bound.argtypes = [vp, C.c_int64]
@@ -89,6 +91,8 @@ def lib():
     L.pac_imdct.argtypes = [vp, dp, C.c_int, C.c_int, dp]
     L.pac_analysis.argtypes = [vp, dp, C.c_int, i32p, i32p, dp, dp, dp, dp]
     L.pac_calc_smrs.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp]
+    L.pac_masked_threshold.argtypes = [vp, dp, C.c_int, C.c_int, dp]
+    L.pac_huffman_select.argtypes = [vp, C.POINTER(C.c_uint32), i32p, C.c_int, i32p, i64p]
     L.pac_bitalloc.argtypes = [vp, C.c_int, dp, i64p, C.c_int, dp, i32p, i32p, i64p]
     L.pac_scale_factor.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, i32p]
     L.pac_vquantize_uniform.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
@@ -208,6 +212,17 @@ class Engine(object):
     @property
     def launches(self):
         return int(lib().pac_launch_count(self.ctx))
+
+    KINDS = ("analysis", "scan", "pack", "index", "unpack", "synth")
+
+    def timing(self, on=True):
+        self._ck(lib().pac_timing_enable(self.ctx, 1 if on else 0))
+
+    def timing_get(self):
+        """{kernel kind: (total device ms, launches)} since timing(True)"""
+        ms = np.zeros(8); cnt = np.zeros(8, np.int64)
+        self._ck(lib().pac_timing_get(self.ctx, _p(ms, C.c_double), _p(cnt, C.c_int64)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KINDS)}
 
     # ---------------------------------------------------------------- whole streams
     def num_blocks(self, nSamples):
@@ -362,6 +377,18 @@ class Engine(object):
         smr = np.zeros((data.shape[0], self.nBands))
         self._ck(lib().pac_calc_smrs(self.ctx, _p(data, C.c_double), _p(mdct, C.c_double), data.shape[0], int(scale), _p(smr, C.c_double)))
         return smr
+
+    def masked_threshold(self, data, noDrop=False):
+        data = np.ascontiguousarray(data, np.float64).reshape(-1, self.N)
+        thr = np.zeros((data.shape[0], self.M))
+        self._ck(lib().pac_masked_threshold(self.ctx, _p(data, C.c_double), data.shape[0], 1 if noDrop else 0, _p(thr, C.c_double)))
+        return thr
+
+    def huffman_select(self, mags, ba_per_symbol):
+        mags = np.ascontiguousarray(mags, np.uint32); ba = np.ascontiguousarray(ba_per_symbol, np.int32)
+        tid = C.c_int32(); tot = np.zeros(NTABLES, np.int64)
+        self._ck(lib().pac_huffman_select(self.ctx, _p(mags, C.c_uint32), _p(ba, C.c_int32), len(mags), C.byref(tid), _p(tot, C.c_int64)))
+        return int(tid.value), tot
 
     def bitalloc(self, bitBudget, extraBits, maxMantBits, smr, lrms_mask):
         smr = np.ascontiguousarray(smr, np.float64).reshape(-1, self.nBands)

@@ -34,6 +34,7 @@ struct AnalysisArgs {
     T *dbg_mdct;                 // [nwork][2][M]  (optional) scaled L/R lines
     T *dbg_bthr;                 // [nwork][6][M]  (optional) L,R,M,S,M',S' thresholds in dB
     DevTables<T> tab;
+    DevTables<double> tabd;      // double tables: fp32 mode computes the MDCT in fp64 and splits Bark values hi+lo
     BandInfo bands;
 };
 
@@ -48,6 +49,7 @@ struct AnalysisSmem {
     T Lb[2][M];            // scaled MDCT lines L, R
     T P[M + 8];            // |spectrum|^2 of the current curve
     T mz[M / 2], mp[M / 2], ml[M / 2];   // masker list: Bark position, SPL, 0.367*max(SPL-40,0)
+    T mzlo[M / 2];                       // fp32 mode: low part of the masker's Bark position
     T red[64];
     int wsum[NT / 32 + 1];
     int cnt;
@@ -57,7 +59,8 @@ struct AnalysisSmem {
 
 // spread + accumulate one masker into 4 lines.  fp64 keeps the reference's operation order
 // (psychoac.py:111-120); fp32 folds the constants and uses ex2.approx.
-__device__ __forceinline__ void spread4(double (&acc)[4], const double (&zl)[4], double zm, double pm, double lev, double drop) {
+__device__ __forceinline__ void spread4(double (&acc)[4], const double (&zl)[4], const double (&)[4], double zm, double,
+                                        double pm, double lev, double drop) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         double dz = zl[j] - zm;
@@ -72,19 +75,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void spread4(float (&acc)[4], const float (&zl)[4], float zm, float pm, float lev, float drop) {
+__device__ __forceinline__ void spread4(float (&acc)[4], const float (&zl)[4], const float (&zlo)[4], float zm, float zmlo,
+                                        float pm, float lev, float drop) {
     const float K = 0.33219280948873623f;           // log2(10)/10
     float c0 = (pm - drop - 96.0f) * K;
     float up = (lev - 27.0f) * K, dn = -27.0f * K;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        float dz = zl[j] - zm;
+        float dz = (zl[j] - zm) + (zlo[j] - zmlo);  // Bark distance from hi+lo pairs (a single fp32 costs 3e-5 dB)
         float a = fmaxf(fabsf(dz) - 0.5f, 0.0f);
         float sl = dz >= 0.0f ? up : dn;
         acc[j] += ex2_approx(fmaf(sl, a, c0));
     }
 }
-
 
 // DFT of hann*y at bin k (0 <= k < M) from F = DFT(y)[0..M], y real:  .5 F[k] - .25 (w F[k-1] + conj(w) F[k+1])
 template <typename T>
@@ -102,7 +105,8 @@ __device__ __forceinline__ typename Vec2<T>::type hann_tap(const typename Vec2<T
 // -> dB.  All threads of the CTA must call; uses sm.P / sm.mz / sm.mp / sm.ml / sm.wsum / sm.cnt.
 template <typename T, int LOGM, class Spec>
 __device__ __forceinline__ void masked_curve(AnalysisSmem<T, LOGM> &sm, const DevTables<T> &tb, Spec spec, T drop,
-                                             const T (&zl)[4], const T (&tiq)[4], T (&thr)[4]) {
+                                             const T (&zl)[4], const T (&zlo)[4], const T (&tiq)[4], const double *zpeakd,
+                                             T (&thr)[4]) {
     using T2 = typename Vec2<T>::type;
     constexpr int M = 1 << LOGM, NT = M / 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,14 +153,16 @@ __device__ __forceinline__ void masked_curve(AnalysisSmem<T, LOGM> &sm, const De
             }
             T pmv = spl_of<T>(tb.cnorm * ssum);
             T lv = (T)0.367 * (pmv - (T)40 > 0 ? pmv - (T)40 : (T)0);     // :114
-            sm.mz[offs] = tb.zpeak[k]; sm.mp[offs] = pmv; sm.ml[offs] = lv;
+            const double zp = zpeakd[k];
+            const T zph = (T)zp;
+            sm.mz[offs] = zph; sm.mzlo[offs] = (T)(zp - (double)zph); sm.mp[offs] = pmv; sm.ml[offs] = lv;
             offs++;
         }
     }
     __syncthreads();
     const int cnt = sm.cnt;
     T acc[4] = {0, 0, 0, 0};
-    for (int m = 0; m < cnt; m++) spread4(acc, zl, sm.mz[m], sm.mp[m], sm.ml[m], drop);
+    for (int m = 0; m < cnt; m++) spread4(acc, zl, zlo, sm.mz[m], sm.mzlo[m], sm.mp[m], sm.ml[m], drop);
 #pragma unroll
     for (int j = 0; j < 4; j++) thr[j] = spl_of<T>(acc[j] + tiq[j]);      // :454-456
     __syncthreads();
@@ -177,12 +183,14 @@ k_analysis(const AnalysisArgs<T> a) {
     constexpr int XS = N + 4;
 
     // per-thread constants for its 4 lines i = tid + NT*j
-    T zl[4], tiq[4], mld[4];
+    T zl[4], zlo[4], tiq[4], mld[4];
     int bnd[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int i = tid + NT * j;
-        zl[j] = tb.zline[i]; tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
+        const double zd = a.tabd.zline[i];
+        zl[j] = (T)zd; zlo[j] = (T)(zd - (double)zl[j]);
+        tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
     }
 
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
@@ -250,25 +258,69 @@ k_analysis(const AnalysisArgs<T> a) {
             xt[ch * XS + n] *= tb.sinw[n];
         }
         __syncthreads();
-        for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
-            int ch = e / H, n = e - ch * H;
-            const T *x = xt + ch * XS;
-            int m0 = 2 * n, m1 = M - 1 - 2 * n;
-            T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
-            T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
-            sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
-        }
-        __syncthreads();
-        fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
         T mx[2] = {0, 0};
-        for (int e = tid; e < 2 * H; e += NT) {
-            int ch = e / H, k = e - ch * H;
-            T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
-            T v0 = ((T)2 / (T)N) * y.x, v1 = -((T)2 / (T)N) * y.y;
-            sm.Lb[ch][2 * k] = v0;
-            sm.Lb[ch][M - 1 - 2 * k] = v1;
-            T m = fmax(fabs(v0), fabs(v1));
-            if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
+        if constexpr (sizeof(T) == 8) {
+            for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
+                int ch = e / H, n = e - ch * H;
+                const T *x = xt + ch * XS;
+                int m0 = 2 * n, m1 = M - 1 - 2 * n;
+                T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
+                T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
+                sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
+            }
+            __syncthreads();
+            fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
+            for (int e = tid; e < 2 * H; e += NT) {
+                int ch = e / H, k = e - ch * H;
+                T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+                T v0 = ((T)2 / (T)N) * y.x, v1 = -((T)2 / (T)N) * y.y;
+                sm.Lb[ch][2 * k] = v0;
+                sm.Lb[ch][M - 1 - 2 * k] = v1;
+                T m = fmax(fabs(v0), fabs(v1));
+                if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
+            }
+        } else {
+            // fp32 mode: an fp32 FFT leaves an error floor of ~1e-7 x (largest line) on EVERY line, i.e. far more than
+            // 1e-5 relative on the weak high-frequency lines.  The MDCT is ~1% of the block's work, so it is done in
+            // fp64 straight from the source samples (re-read through L1/L2) and only then rounded to fp32.
+            double2 *Wd = reinterpret_cast<double2 *>(&sm.W[0][0]);       // [2][H] double2 = 16 KB <= sizeof(W)
+            const DevTables<double> &td = a.tabd;
+            auto xd = [&](int ch, int n) -> double {
+                double v;
+                if (a.pcm) {
+                    const int64_t ns = a.nSamples[s];
+                    const int64_t si = (int64_t)(b - 1) * M + n;
+                    int pv = (si >= 0 && si < ns) ? __ldg(reinterpret_cast<const int *>(a.pcm) + (int64_t)s * a.strideSamples + si) : 0;
+                    int c = ch ? (pv >> 16) : (int)(short)(pv & 0xffff);
+                    int code = c < 0 ? -c : c;
+                    if (code & 32768) code -= 32768;
+                    v = 2.0 * (double)code / 65535.0;
+                    if (c < 0) v = -v;
+                } else v = a.blocks[w * 2 * N + ch * N + n];
+                return v * td.sinw[n];
+            };
+            for (int e = tid; e < 2 * H; e += NT) {
+                int ch = e / H, n = e - ch * H;
+                int m0 = 2 * n, m1 = M - 1 - 2 * n;
+                double u0 = m0 < H ? -xd(ch, 3 * H - 1 - m0) - xd(ch, 3 * H + m0) : xd(ch, m0 - H) - xd(ch, 2 * H - 1 - (m0 - H));
+                double u1 = m1 < H ? -xd(ch, 3 * H - 1 - m1) - xd(ch, 3 * H + m1) : xd(ch, m1 - H) - xd(ch, 2 * H - 1 - (m1 - H));
+                Wd[ch * H + n] = cmul(mk2<double>(u0, u1), td.mdct_pre[n]);
+            }
+            __syncthreads();
+            fft_dif<double, LOGM - 1, NT>(Wd, 2, H, td.tw, 2);
+            double mxd[2] = {0, 0};
+            for (int e = tid; e < 2 * H; e += NT) {
+                int ch = e / H, k = e - ch * H;
+                double2 y = cmul(Wd[ch * H + fft_pos<LOGM - 1>(k)], td.mdct_post[k]);
+                double v0 = (2.0 / (double)N) * y.x, v1 = -(2.0 / (double)N) * y.y;
+                // kept in fp32 up to the power-of-two overall scale: rounding to fp32 commutes with that scaling
+                sm.Lb[ch][2 * k] = (T)v0;
+                sm.Lb[ch][M - 1 - 2 * k] = (T)v1;
+                double m = fmax(fabs(v0), fabs(v1));
+                if (ch == 0) mxd[0] = fmax(mxd[0], m); else mxd[1] = fmax(mxd[1], m);
+            }
+            mx[0] = (T)mxd[0]; mx[1] = (T)mxd[1];
+            // the overall scale only needs max|line|; its fp32 rounding can move the quantiser boundary by 6e-8 relative
         }
         mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
         if (lane == 0) { sm.red[warp] = mx[0]; sm.red[32 + warp] = mx[1]; }
@@ -318,12 +370,12 @@ k_analysis(const AnalysisArgs<T> a) {
         __syncthreads();
         // ------------------------------------------------ E. six masked-threshold curves
         T thr[6][4];
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, tiq, thr[0]);   // BTHR_L  :540
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[1][k]; }, (T)15, zl, tiq, thr[1]);   // BTHR_R  :541
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[0][k]; }, (T)15, zl, tiq, thr[2]);    // BTHR_M  :559
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[1][k]; }, (T)15, zl, tiq, thr[3]);    // BTHR_S  :560
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[0], k, hw, hwc); }, (T)0, zl, tiq, thr[4]);   // :561
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, tiq, thr[5]);   // :562
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[0]);   // BTHR_L  :540
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[1]);   // BTHR_R  :541
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[2]);    // BTHR_M  :559
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[3]);    // BTHR_S  :560
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[0], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[4]);   // :561
+        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[5]);   // :562
         // ------------------------------------------------ F. SMR candidates, band maxima, select
         const uint32_t lrms = sm.lrms;
         T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
@@ -403,10 +455,11 @@ template <typename T>
 struct SmrMonoArgs {
     const double *data;      // [n][N] time samples (Hann applied here, psychoac.py:225)
     const double *mdct;      // [n][M] lines scaled by 2^scale
-    int n, scale;
-    double *smr;             // [n][kMaxBands]
+    int n, scale, noDrop;
+    double *smr;             // [n][kMaxBands] (may be NULL)
     double *thr;             // [n][M] optional masked threshold (getMaskedThreshold)
     DevTables<T> tab;
+    DevTables<double> tabd;
     BandInfo bands;
 };
 
@@ -420,9 +473,13 @@ k_calc_smrs(const SmrMonoArgs<T> a) {
     S &sm = *reinterpret_cast<S *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables<T> &tb = a.tab;
-    T zl[4], tiq[4];
+    T zl[4], zlo[4], tiq[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) { zl[j] = tb.zline[tid + NT * j]; tiq[j] = tb.tiq[tid + NT * j]; }
+    for (int j = 0; j < 4; j++) {
+        const double zd = a.tabd.zline[tid + NT * j];
+        zl[j] = (T)zd; zlo[j] = (T)(zd - (double)zl[j]);
+        tiq[j] = tb.tiq[tid + NT * j];
+    }
     const int w = blockIdx.x;
     for (int m = tid; m < M; m += NT) {
         T x0 = (T)a.data[(int64_t)w * N + 2 * m] * tb.hann[2 * m];
@@ -434,16 +491,19 @@ k_calc_smrs(const SmrMonoArgs<T> a) {
     for (int k = tid; k <= M; k += NT) sm.XF[0][k] = rfft_split<T, LOGM>(sm.W[0], k, tb.tw_split);
     __syncthreads();
     T thr[4];
-    masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, tiq, thr);
+    masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, a.noDrop ? (T)0 : (T)15, zl, zlo, tiq, a.tabd.zpeak, thr);
     T *V = reinterpret_cast<T *>(&sm.W[0][0]);
     const T sc = (T)exp2((double)a.scale);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int i = tid + NT * j;
-        T tr = (T)a.mdct[(int64_t)w * M + i] / sc;                 // :285
-        V[i] = spl_of<T>((T)4 * (tr * tr)) - thr[j];                // :286-287, :316
         if (a.thr) a.thr[(int64_t)w * M + i] = (double)thr[j];
+        if (a.smr) {
+            T tr = (T)a.mdct[(int64_t)w * M + i] / sc;             // :285
+            V[i] = spl_of<T>((T)4 * (tr * tr)) - thr[j];            // :286-287, :316
+        }
     }
+    if (!a.smr) return;
     __syncthreads();
     for (int bd = warp; bd < a.bands.nBands; bd += NW) {
         T v = -INFINITY;

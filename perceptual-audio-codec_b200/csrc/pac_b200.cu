@@ -58,6 +58,13 @@ struct PacCtx {
     std::string err;
     int64_t launches = 0;
     int numSMs = 148;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int kind; };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> evpool;
+    double kms[PAC_NKINDS] = {0};
+    int64_t kcount[PAC_NKINDS] = {0};
     // constant tables per N (the context's own N plus any N the L2 entry points were asked for)
     std::map<int, TableSet<float>> tf;
     std::map<int, TableSet<double>> td;
@@ -92,6 +99,46 @@ struct PacCtx {
         ctx->err = b_;                                    \
         return (code);                                    \
     } while (0)
+
+
+// ------------------------------------------------------------------ per-kernel timing
+static cudaEvent_t ev_get(PacCtx *ctx) {
+    if (!ctx->evpool.empty()) { cudaEvent_t e = ctx->evpool.back(); ctx->evpool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+static void timing_flush(PacCtx *ctx) {      // call only after the stream has been synchronised
+    for (auto &p : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { ctx->kms[p.kind] += ms; ctx->kcount[p.kind]++; }
+        ctx->evpool.push_back(p.a); ctx->evpool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+struct KTimer {
+    PacCtx *ctx; int kind; cudaEvent_t a{}, b{};
+    KTimer(PacCtx *c, int k) : ctx(c), kind(k) { if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, ctx->stream); } }
+    ~KTimer() { if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->pending.push_back({a, b, kind}); } }
+};
+
+extern "C" int pac_timing_enable(PacCtx *ctx, int on) {
+    if (!ctx) return PAC_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    timing_flush(ctx);
+    ctx->timing = on != 0;
+    for (int i = 0; i < PAC_NKINDS; i++) { ctx->kms[i] = 0; ctx->kcount[i] = 0; }
+    return PAC_OK;
+}
+extern "C" int pac_timing_get(PacCtx *ctx, double *ms, int64_t *count) {
+    if (!ctx || !ms || !count) return PAC_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    timing_flush(ctx);
+    for (int i = 0; i < PAC_NKINDS; i++) { ms[i] = ctx->kms[i]; count[i] = ctx->kcount[i]; }
+    return PAC_OK;
+}
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
@@ -338,7 +385,8 @@ extern "C" int pac_ctx_create(int device, int precision, const PacParams *params
 extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); timing_flush(ctx); cudaStreamDestroy(ctx->stream); }
+    for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
     for (auto &kv : ctx->winTables) cudaFree(kv.second);
@@ -411,7 +459,7 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     int64_t grid = (int64_t)ctx->numSMs * perSM;
     if (grid > a.nwork) grid = a.nwork;
     if (grid < 1) grid = 1;
-    k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a);
+    { KTimer kt(ctx, PAC_K_ANALYSIS); k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -423,6 +471,7 @@ static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
     a.nScaleBits = ctx->p.nScaleBits;
     int rc = get_tables<T>(ctx, ctx->N, &a.tab);
     if (rc) return rc;
+    if ((rc = get_tables<double>(ctx, ctx->N, &a.tabd))) return rc;
     if (ctx->LOGM == 10) return launch_analysis_t<T, 10>(ctx, a);
     if (ctx->LOGM == 9) return launch_analysis_t<T, 9>(ctx, a);
     FAIL(PAC_E_ARG, "unsupported nMDCTLines");
@@ -432,7 +481,7 @@ template <typename T>
 static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
     a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.lenLut = ctx->lenLut;
     constexpr int WARPS = 4;
-    k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, ctx->stream>>>(a);
+    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, ctx->stream>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -446,7 +495,7 @@ static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
     int64_t maxg = (int64_t)ctx->numSMs * 8;
     if (grid > maxg) grid = maxg;
     if (grid < 1) grid = 1;
-    k_pack<T><<<(unsigned)grid, kPackWarps * 32, 0, ctx->stream>>>(a);
+    { KTimer kt(ctx, PAC_K_PACK); k_pack<T><<<(unsigned)grid, kPackWarps * 32, 0, ctx->stream>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -621,7 +670,7 @@ template <typename T, int LOGM>
 static int launch_synth_t(PacCtx *ctx, SynthArgs<T> &a, int64_t grid) {
     size_t smem = sizeof(SynthSmem<T, LOGM>);
     CK(cudaFuncSetAttribute(k_synth<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_synth<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a);
+    { KTimer kt(ctx, PAC_K_SYNTH); k_synth<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -691,7 +740,7 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff
     ia.pac = d_pac; ia.pacOff = ctx->w_ns.as<int64_t>(); ia.S = S; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
     ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
     ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
-    k_index<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ia);
+    { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ia); }
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<int32_t> nblk(S), stt(S);
@@ -716,7 +765,7 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff
         int64_t nchunk = nblkAll * 2;
         int64_t grid = (nchunk + 63) / 64;
         if (grid > (int64_t)ctx->numSMs * 32) grid = (int64_t)ctx->numSMs * 32;
-        k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua);
+        { KTimer kt(ctx, PAC_K_UNPACK); k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua); }
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -1109,28 +1158,65 @@ extern "C" int pac_analysis(PacCtx *ctx, const double *data, int nblk, int32_t *
 }
 
 template <typename T, int LOGM>
-static int calc_smrs_t(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr) {
+static int calc_smrs_t(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr, int noDrop, double *thr) {
     constexpr int M = 1 << LOGM, N = 2 * M;
     const int NB = ctx->bands.nBands;
     CK(ctx->w_misc.ensure((size_t)n * N * 8));
     CK(ctx->w_misc2.ensure((size_t)n * M * 8));
     CK(ctx->w_misc3.ensure((size_t)n * kMaxBands * 8));
+    CK(ctx->w_misc4.ensure((size_t)n * M * 8));
     CK(cudaMemcpyAsync(ctx->w_misc.p, data, (size_t)n * N * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->w_misc2.p, mdct, (size_t)n * M * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (mdct) CK(cudaMemcpyAsync(ctx->w_misc2.p, mdct, (size_t)n * M * 8, cudaMemcpyHostToDevice, ctx->stream));
     SmrMonoArgs<T> a{};
-    a.data = ctx->w_misc.as<double>(); a.mdct = ctx->w_misc2.as<double>(); a.n = n; a.scale = scale;
-    a.smr = ctx->w_misc3.as<double>(); a.thr = nullptr; a.bands = ctx->bands;
+    a.data = ctx->w_misc.as<double>(); a.mdct = ctx->w_misc2.as<double>(); a.n = n; a.scale = scale; a.noDrop = noDrop;
+    a.smr = smr ? ctx->w_misc3.as<double>() : nullptr; a.thr = thr ? ctx->w_misc4.as<double>() : nullptr; a.bands = ctx->bands;
     int rc = get_tables<T>(ctx, N, &a.tab);
     if (rc) return rc;
+    if ((rc = get_tables<double>(ctx, N, &a.tabd))) return rc;
     size_t smem = sizeof(AnalysisSmem<T, LOGM>);
     CK(cudaFuncSetAttribute(k_calc_smrs<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_calc_smrs<T, LOGM><<<n, M / 4, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<double> hs((size_t)n * kMaxBands);
-    CK(cudaMemcpyAsync(hs.data(), a.smr, hs.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (smr) CK(cudaMemcpyAsync(hs.data(), a.smr, hs.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (thr) CK(cudaMemcpyAsync(thr, a.thr, (size_t)n * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n; i++) for (int bd = 0; bd < NB; bd++) smr[(size_t)i * NB + bd] = hs[(size_t)i * kMaxBands + bd];
+    if (smr) for (int i = 0; i < n; i++) for (int bd = 0; bd < NB; bd++) smr[(size_t)i * NB + bd] = hs[(size_t)i * kMaxBands + bd];
+    return PAC_OK;
+}
+
+static int calc_smrs_dispatch(PacCtx *ctx, const double *data, const double *mdct, int n, int scale, double *smr, int noDrop, double *thr) {
+    const bool f64 = ctx->precision == PAC_PRECISION_FP64;
+    if (ctx->LOGM == 10) return f64 ? calc_smrs_t<double, 10>(ctx, data, mdct, n, scale, smr, noDrop, thr) : calc_smrs_t<float, 10>(ctx, data, mdct, n, scale, smr, noDrop, thr);
+    if (ctx->LOGM == 9) return f64 ? calc_smrs_t<double, 9>(ctx, data, mdct, n, scale, smr, noDrop, thr) : calc_smrs_t<float, 9>(ctx, data, mdct, n, scale, smr, noDrop, thr);
+    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+}
+
+extern "C" int pac_masked_threshold(PacCtx *ctx, const double *data, int n, int noDrop, double *thr) {
+    if (!ctx) return PAC_E_ARG;
+    if (!data || !thr || n <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_masked_threshold");
+    CK(cudaSetDevice(ctx->device));
+    return calc_smrs_dispatch(ctx, data, nullptr, n, 0, nullptr, noDrop, thr);
+}
+
+extern "C" int pac_huffman_select(PacCtx *ctx, const uint32_t *mag, const int32_t *ba, int n, int32_t *tableID, int64_t *totals) {
+    if (!ctx) return PAC_E_ARG;
+    if (n < 0 || !tableID || !totals || (n > 0 && (!mag || !ba))) FAIL(PAC_E_ARG, "bad arguments to pac_huffman_select");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w_misc.ensure((size_t)(n + 1) * 4)); CK(ctx->w_misc2.ensure((size_t)(n + 1) * 4));
+    CK(ctx->w_misc3.ensure(4)); CK(ctx->w_misc4.ensure(kNTables * 8));
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->w_misc.p, mag, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->w_misc2.p, ba, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_huff_select<<<1, 256, 0, ctx->stream>>>(ctx->w_misc.as<uint32_t>(), ctx->w_misc2.as<int32_t>(), n, ctx->lenLut, ctx->ec,
+                                            ctx->w_misc3.as<int32_t>(), ctx->w_misc4.as<long long>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tableID, ctx->w_misc3.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(totals, ctx->w_misc4.p, kNTables * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return PAC_OK;
 }
 
@@ -1138,10 +1224,7 @@ extern "C" int pac_calc_smrs(PacCtx *ctx, const double *data, const double *mdct
     if (!ctx) return PAC_E_ARG;
     if (!data || !mdct || !smr || n <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_calc_smrs");
     CK(cudaSetDevice(ctx->device));
-    const bool f64 = ctx->precision == PAC_PRECISION_FP64;
-    if (ctx->LOGM == 10) return f64 ? calc_smrs_t<double, 10>(ctx, data, mdct, n, scale, smr) : calc_smrs_t<float, 10>(ctx, data, mdct, n, scale, smr);
-    if (ctx->LOGM == 9) return f64 ? calc_smrs_t<double, 9>(ctx, data, mdct, n, scale, smr) : calc_smrs_t<float, 9>(ctx, data, mdct, n, scale, smr);
-    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+    return calc_smrs_dispatch(ctx, data, mdct, n, scale, smr, 0, nullptr);
 }
 
 extern "C" int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *extraBits, int maxMantBits,

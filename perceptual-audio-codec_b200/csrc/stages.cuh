@@ -90,6 +90,37 @@ __global__ void k_bitalloc(int n, const double *bitBudget, const long long *extr
     if (lane == 0) diff[p] = d;
 }
 
+// Huffman.encodeData (Huffman.py:274-309) on caller-supplied unsigned mantissas: total code length under each of
+// the 10 tables (escape = escape code + bitAlloc raw bits), strictly-shortest wins, ties keep the lowest ID.
+__global__ void k_huff_select(const uint32_t *mag, const int32_t *ba, int n, const unsigned long long *lenLut, EncConsts ec,
+                              int32_t *tableID, long long *totals /*[kNTables]*/) {
+    __shared__ unsigned long long tot[kNTables];
+    if (threadIdx.x < kNTables) tot[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long loc[kNTables];
+#pragma unroll
+    for (int t = 0; t < kNTables; t++) loc[t] = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned m = mag[i];
+        unsigned long long lw = m < (unsigned)kLenLutSize ? lenLut[m] : 0ull;
+#pragma unroll
+        for (int t = 0; t < kNTables; t++) {
+            unsigned l = (unsigned)(lw >> (5 * t)) & 31u;
+            loc[t] += l ? l : (unsigned)(ec.esc_len[t] + ba[i]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kNTables; t++) atomicAdd(&tot[t], loc[t]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 1;
+        unsigned long long bv = tot[0];
+        for (int t = 1; t < kNTables; t++) if (tot[t] < bv) { bv = tot[t]; best = t + 1; }
+        *tableID = best;
+        for (int t = 0; t < kNTables; t++) totals[t] = (long long)tot[t];
+    }
+}
+
 // quantize.py
 __global__ void k_scale_factor(const double *x, int n, int nScaleBits, int nMantBits, int32_t *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
