@@ -87,6 +87,10 @@ int  pac_band_layout(PacCtx *ctx, int32_t *nLines /*[PAC_MAX_BANDS]*/, int32_t *
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pac_launch_count(PacCtx *ctx);
 
+/* run this context's kernels and copies on the caller's CUDA stream (a cudaStream_t; NULL = the context's own stream),
+ * so that the caller's CUDA events bracket the work. */
+int pac_set_stream(PacCtx *ctx, void *stream);
+
 /* per-kernel device time, measured with CUDA events on the stream the kernels are launched on (bench.py's roofline).
  * kinds index ms[] / count[]; timing adds two event records per launch and is off by default. */
 #define PAC_K_ANALYSIS 0   /* window + MDCT + M/S decision + SMR (analysis.cuh) */

@@ -73,6 +73,7 @@ def lib():
     L.pac_band_layout.argtypes = [vp, i32p, i32p]
     L.pac_launch_count.argtypes = [vp]
     L.pac_launch_count.restype = C.c_int64
+    L.pac_set_stream.argtypes = [vp, vp]
     L.pac_timing_enable.argtypes = [vp, C.c_int]
     L.pac_timing_get.argtypes = [vp, dp, i64p]
     L.pac_num_blocks.argtypes = [vp, C.c_int64]
@@ -214,6 +215,10 @@ class Engine(object):
         return int(lib().pac_launch_count(self.ctx))
 
     KINDS = ("analysis", "scan", "pack", "index", "unpack", "synth")
+
+    def set_stream(self, cuda_stream_handle):
+        """use the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None restores the own stream"""
+        self._ck(lib().pac_set_stream(self.ctx, C.c_void_p(cuda_stream_handle or 0)))
 
     def timing(self, on=True):
         self._ck(lib().pac_timing_enable(self.ctx, 1 if on else 0))

@@ -55,6 +55,7 @@ struct PacCtx {
     int32_t nLines[kMaxBands]{};
     EncConsts ec{};
     cudaStream_t stream = nullptr;
+    cudaStream_t ownStream = nullptr;
     std::string err;
     int64_t launches = 0;
     int numSMs = 148;
@@ -121,6 +122,15 @@ struct KTimer {
     KTimer(PacCtx *c, int k) : ctx(c), kind(k) { if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, ctx->stream); } }
     ~KTimer() { if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->pending.push_back({a, b, kind}); } }
 };
+
+extern "C" int pac_set_stream(PacCtx *ctx, void *stream) {
+    if (!ctx) return PAC_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    timing_flush(ctx);
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->ownStream;
+    return PAC_OK;
+}
 
 extern "C" int pac_timing_enable(PacCtx *ctx, int on) {
     if (!ctx) return PAC_E_ARG;
@@ -363,7 +373,8 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
     ec.nScaleBits = params->nScaleBits; ec.nMantSizeBits = params->nMantSizeBits; ec.nTableIDBits = params->nTableIDBits;
     ec.maxMantBits = (1 << params->nMantSizeBits) > 16 ? 16 : (1 << params->nMantSizeBits);     // codec.py:218-219
     ec.fixedBits = params->nScaleBits + params->nTableIDBits + NB * (params->nMantSizeBits + params->nScaleBits) + NB;
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+    ctx->stream = ctx->ownStream;
     int rc = build_huffman(ctx, tables);
     if (rc) return rc;
     DevTables<float> tf; DevTables<double> td;
@@ -385,7 +396,8 @@ extern "C" int pac_ctx_create(int device, int precision, const PacParams *params
 extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); timing_flush(ctx); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); timing_flush(ctx); }
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);

@@ -60,7 +60,11 @@ def synth_pcm(seed, n, kind="mix"):
     if kind == "mono":
         pcm[:, 1] = pcm[:, 0]
     elif kind == "anti":
-        pcm[:, 1] = -np.maximum(pcm[:, 0], -32767)
+        # R = -L exactly, so M == 0 exactly.  (-32768 is avoided on purpose: it dequantises to 0 (Q21), which would
+        # make M a single impulse = an exactly flat spectrum, where the reference's own peak picking is decided by
+        # the rounding noise of its FFT and no implementation can reproduce it.)
+        pcm[:, 0] = np.maximum(pcm[:, 0], -32767)
+        pcm[:, 1] = -pcm[:, 0]
     elif kind == "left":
         pcm[:, 1] = 0
     elif kind == "silence":
