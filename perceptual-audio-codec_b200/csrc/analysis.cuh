@@ -11,6 +11,8 @@
 // checked there against dumps of the reference.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
+
 #include "fft.cuh"
 
 namespace pac {
@@ -35,10 +37,24 @@ struct AnalysisArgs {
     T *dbg_bthr;                 // [nwork][6][M]  (optional) L,R,M,S,M',S' thresholds in dB
     DevTables<T> tab;
     DevTables<double> tabd;      // double tables: fp32 mode computes the MDCT in fp64 and splits Bark values hi+lo
+    FastTables ft;               // fp32 mode only
     BandInfo bands;
 };
 
-template <typename T, int LOGM>
+// extra shared memory of the fp32 fast threshold evaluation
+template <int LOGM>
+struct FastSmem {
+    static constexpr int M = 1 << LOGM;
+    float Ah[M + M / 4 + M / 16 + M / 64 + 4];   // plateau intensity per bin, then its 4-, 16- and 64-bin block sums
+    float V[M], Wq[M];            // dense per bin: down-scan injection, up-scan injection (quiet maskers)
+    float4 loud[M / 2];           // maskers louder than 40 dB: (c0 - up/2, up, zk_hi, zk_lo)
+    short loudEU[M / 2];          // their first upper-skirt line
+    unsigned short loudPrefix[M + 2];   // number of loud maskers with bin < k
+    float totD[16], totA[16];
+};
+struct NoSmem {};
+
+template <typename T, int LOGM, bool FASTK = false>
 struct AnalysisSmem {
     static constexpr int M = 1 << LOGM;
     static constexpr int N = 2 * M;
@@ -48,13 +64,15 @@ struct AnalysisSmem {
     T2 W[2][M + 2];        // FFT work; later F2_M, F2_S; finally the four per-line SMR candidate arrays
     T Lb[2][M];            // scaled MDCT lines L, R
     T P[M + 8];            // |spectrum|^2 of the current curve
-    T mz[M / 2], mp[M / 2], ml[M / 2];   // masker list: Bark position, SPL, 0.367*max(SPL-40,0)
-    T mzlo[M / 2];                       // fp32 mode: low part of the masker's Bark position
+    static constexpr int MLM = FASTK ? 1 : M / 2;                // the direct evaluation's masker list (fp64 / mono kernels)
+    T mz[MLM], mp[MLM], ml[MLM];         // Bark position, SPL, 0.367*max(SPL-40,0)
+    T mzlo[MLM];                         // (low part of the Bark position when T = float)
     T red[64];
     int wsum[NT / 32 + 1];
     int cnt;
     uint32_t lrms;
     int oscale[2];
+    typename std::conditional<FASTK, FastSmem<LOGM>, NoSmem>::type fs;
 };
 
 // spread + accumulate one masker into 4 lines.  fp64 keeps the reference's operation order
@@ -103,8 +121,8 @@ __device__ __forceinline__ typename Vec2<T>::type hann_tap(const typename Vec2<T
 // One masked-threshold curve (calcBTHR body after the FFT, psychoac.py:431-456): power spectrum from `spec`,
 // findpeaks (:158-191), masker SPLs (:448), spreading over this thread's 4 lines (:447-452), + threshold in quiet,
 // -> dB.  All threads of the CTA must call; uses sm.P / sm.mz / sm.mp / sm.ml / sm.wsum / sm.cnt.
-template <typename T, int LOGM, class Spec>
-__device__ __forceinline__ void masked_curve(AnalysisSmem<T, LOGM> &sm, const DevTables<T> &tb, Spec spec, T drop,
+template <typename T, int LOGM, class SMEM, class Spec>
+__device__ __forceinline__ void masked_curve(SMEM &sm, const DevTables<T> &tb, Spec spec, T drop,
                                              const T (&zl)[4], const T (&zlo)[4], const T (&tiq)[4], const double *zpeakd,
                                              T (&thr)[4]) {
     using T2 = typename Vec2<T>::type;
@@ -168,10 +186,249 @@ __device__ __forceinline__ void masked_curve(AnalysisSmem<T, LOGM> &sm, const De
     __syncthreads();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 fast threshold curve.  Same quantity as masked_curve (calcBTHR, psychoac.py:431-456) but the fixed-slope parts
+// of the spreading function are evaluated by weighted scans over the lines (static weights), the plateau by range
+// sums over bins (4-level block sums), and only the upper skirts of maskers louder than 40 dB pairwise -- over the
+// lines above them only.  tests/model_analysis.py:curve_v2 is the numpy statement of exactly this procedure.
+// Scans: thread t owns lines 4t..4t+3; pairwise part: warp w owns half-chunks w and 2NW-1-w (2 lines per lane each).
+// Deliberately NOT inlined: it is called six times per block and the kernel must stay inside the instruction cache.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// SPL(intensity) with lg2.approx (abs error ~7e-7 dB)
+__device__ __forceinline__ float spl_fast(float inten) {
+    inten = fmaxf(inten, 2.511886431509582e-13f);
+    return fmaxf(fmaf(lg2_approx(inten), 3.0102999566398120f, 96.0f), -30.0f);
+}
+
+__device__ __forceinline__ float spl_any(float i) { return spl_fast(i); }
+__device__ __forceinline__ double spl_any(double i) { return spl_of<double>(i); }
+
+template <int LOGM>
+__device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, const float2 *F, int tap, float drop,
+                                                 const DevTables<float> *tbp, const FastTables *ftp, const double *zpeakd,
+                                                 const double *zlined, int lb0, int lb1) {
+    constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
+    constexpr int O4 = M, O16 = M + M / 4, O64 = M + M / 4 + M / 16;
+    const DevTables<float> &tb = *tbp;
+    const FastTables &ft = *ftp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float K = 0.33219280948873623f;           // log2(10)/10
+    auto &fs = sm.fs;
+    // 1. power spectrum (optionally of the Hann-tapped spectrum)
+    {
+        const float2 hw = tb.hann_w, hwc = cconj(tb.hann_w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int k = tid + NT * j;
+            float2 v = tap ? hann_tap<float>(F, k, hw, hwc) : F[k];
+            sm.P[k] = v.x * v.x + v.y * v.y;
+        }
+    }
+    __syncthreads();
+    // 2. findpeaks on this thread's 4 bins; dense A / V / Wq; ordered list of the loud maskers
+    const int k0 = 4 * tid;
+    unsigned loudf = 0;
+    float c0s[4], ups[4];
+    {
+        float pw[10];                                 // P[k0-3 .. k0+6]; P[M..M+7] are kept zero
+#pragma unroll
+        for (int q = 0; q < 10; q++) { int kk = k0 - 3 + q; pw[q] = kk >= 0 ? sm.P[kk] : 0.f; }
+        float a4 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = k0 + q;
+            const float pc = pw[q + 3];
+            const bool pk = k >= 1 && k <= M - 2 && pc > pw[q + 2] && pc > pw[q + 4] && pc > 1e-6f;
+            float Av = 0.f, Vv = 0.f, Wv = 0.f;
+            c0s[q] = 0.f; ups[q] = 0.f;
+            if (pk) {
+                // X_fft[k-3:k+3] with python slice semantics (psychoac.py:448): empty for k < 3
+                float ssum = k >= 3 ? ((((pw[q] + pw[q + 1]) + pw[q + 2]) + pw[q + 3]) + pw[q + 4]) + pw[q + 5] : 0.f;
+                const float pmv = spl_fast(tb.cnorm * ssum);
+                const float c0 = (pmv - drop - 96.0f) * K;
+                const float lev = 0.367f * fmaxf(pmv - 40.0f, 0.f);
+                Av = ex2_approx(c0);
+                const int el = ft.eL[k], eu = ft.eU[k];
+                if (el >= 0) Vv = ex2_approx(c0 + ft.xL[k]);
+                if (eu < M) {
+                    if (lev > 0.f) { loudf |= 1u << q; ups[q] = (lev - 27.0f) * K; c0s[q] = c0; }
+                    else Wv = ex2_approx(c0 + ft.xU[k]);
+                }
+            }
+            fs.Ah[k] = Av; fs.V[k] = Vv; fs.Wq[k] = Wv;
+            a4 += Av;
+        }
+        fs.Ah[O4 + tid] = a4;
+    }
+    int nl = __popc(loudf), incl = nl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    int offs = incl - nl;
+    for (int i = 0; i < warp; i++) offs += sm.wsum[i];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        fs.loudPrefix[k0 + q] = (unsigned short)offs;
+        if (loudf & (1u << q)) {
+            const int k = k0 + q;
+            const double zp = zpeakd[k];
+            const float zph = (float)zp;
+            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], zph, (float)(zp - (double)zph));
+            fs.loudEU[offs] = ft.eU[k];
+            offs++;
+        }
+    }
+    if (tid == NT - 1) { fs.loudPrefix[M] = (unsigned short)offs; fs.loudPrefix[M + 1] = (unsigned short)offs; }
+    if (tid < M / 16) {
+        const float *p4 = fs.Ah + O4 + 4 * tid;
+        fs.Ah[O16 + tid] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+    }
+    if (tid >= NT - M / 64) {
+        const float *p4 = fs.Ah + O4 + 16 * (tid - (NT - M / 64));
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) s += p4[q];
+        fs.Ah[O64 + tid - (NT - M / 64)] = s;
+    }
+    __syncthreads();
+    // 3. per-line gathers (deterministic order) + plateau + the two scans; thread t owns lines 4t .. 4t+3
+    {
+        float uD[4], uA[4], pl[4];
+        int pa[4], pb[4];
+        const short *lt = ft.lineTab + 4 * tid;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int kLa = lt[0 * M + q], nL = lt[1 * M + q], kUa = lt[2 * M + q], nU = lt[3 * M + q];
+            uD[q] = (nL > 0 ? fs.V[kLa] : 0.f) + (nL > 1 ? fs.V[kLa + 1] : 0.f) + (nL > 2 ? fs.V[kLa + 2] : 0.f);
+            uA[q] = (nU > 0 ? fs.Wq[kUa] : 0.f) + (nU > 1 ? fs.Wq[kUa + 1] : 0.f) + (nU > 2 ? fs.Wq[kUa + 2] : 0.f);
+            pa[q] = lt[4 * M + q];
+            pb[q] = lt[5 * M + q];
+        }
+        // plateau: the 4 windows [pa_q, pb_q) slide monotonically: sum their common core [pa_3, pb_0) once through the
+        // block-sum pyramid (1, 4, 16, 64 bins) and add each line's few extra bins at either end
+        {
+            float core = 0.f;
+            int k = pa[3];
+            const int ke = pb[0];
+            const bool hascore = k < ke;
+            if (hascore) {
+                while (k < ke && (k & 3)) core += fs.Ah[k++];
+                while (k + 4 <= ke && (k & 15)) { core += fs.Ah[O4 + (k >> 2)]; k += 4; }
+                while (k + 16 <= ke && (k & 63)) { core += fs.Ah[O16 + (k >> 4)]; k += 16; }
+                while (k + 64 <= ke) { core += fs.Ah[O64 + (k >> 6)]; k += 64; }
+                while (k + 16 <= ke) { core += fs.Ah[O16 + (k >> 4)]; k += 16; }
+                while (k + 4 <= ke) { core += fs.Ah[O4 + (k >> 2)]; k += 4; }
+                while (k < ke) core += fs.Ah[k++];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float s = 0.f;
+                if (hascore) {
+                    for (int kk = pa[q]; kk < pa[3]; kk++) s += fs.Ah[kk];
+                    s += core;
+                    for (int kk = pb[0]; kk < pb[q]; kk++) s += fs.Ah[kk];
+                } else {
+                    for (int kk = pa[q]; kk < pb[q]; kk++) s += fs.Ah[kk];
+                }
+                pl[q] = s;
+            }
+        }
+        // descending scan: low[i] = sum_{j >= i} uD[j] 2^{dn (z_j - z_i)}
+        const float *w = ft.sD + tid;
+        float a3 = uD[3];
+        float a2 = fmaf(a3, w[2 * NT], uD[2]);
+        float a1 = fmaf(a2, w[1 * NT], uD[1]);
+        float a0 = fmaf(a1, w[0 * NT], uD[0]);
+        float g = a0;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            float v = __shfl_down_sync(0xffffffffu, g, 1 << s);
+            if (lane + (1 << s) < 32) g = fmaf(v, w[(3 + s) * NT], g);
+        }
+        float gn = __shfl_down_sync(0xffffffffu, g, 1);
+        if (lane == 31) gn = 0.f;
+        if (lane == 0) fs.totD[warp] = g;
+        // ascending scan: up[i] = sum_{j <= i} uA[j] 2^{dn (z_i - z_j)}
+        const float *wa = ft.sA + tid;
+        float b0 = uA[0];
+        float b1 = fmaf(b0, w[0 * NT], uA[1]);
+        float b2 = fmaf(b1, w[1 * NT], uA[2]);
+        float b3 = fmaf(b2, w[2 * NT], uA[3]);
+        float h = b3;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            float v = __shfl_up_sync(0xffffffffu, h, 1 << s);
+            if (lane >= (1 << s)) h = fmaf(v, wa[s * NT], h);
+        }
+        float hp = __shfl_up_sync(0xffffffffu, h, 1);
+        if (lane == 0) hp = 0.f;
+        if (lane == 31) fs.totA[warp] = h;
+        __syncthreads();
+        float C = 0.f;
+        for (int c2 = NW - 1; c2 > warp; c2--) C = fmaf(C, ft.omD[c2], fs.totD[c2]);
+        float inc = fmaf(C, w[8 * NT], gn);
+        pl[0] += fmaf(inc, w[9 * NT], a0);
+        pl[1] += fmaf(inc, w[10 * NT], a1);
+        pl[2] += fmaf(inc, w[11 * NT], a2);
+        pl[3] += fmaf(inc, w[12 * NT], a3);
+        C = 0.f;
+        for (int c2 = 0; c2 < warp; c2++) C = fmaf(C, ft.omA[c2], fs.totA[c2]);
+        inc = fmaf(C, wa[5 * NT], hp);
+        pl[0] += fmaf(inc, wa[6 * NT], b0);
+        pl[1] += fmaf(inc, wa[7 * NT], b1);
+        pl[2] += fmaf(inc, wa[8 * NT], b2);
+        pl[3] += fmaf(inc, wa[9 * NT], b3);
+        // P is dead (all peak work happened before the previous barrier): reuse it to hand the partial thresholds over
+        *reinterpret_cast<float4 *>(&sm.P[4 * tid]) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+    }
+    __syncthreads();
+    // 4. upper skirts of the loud maskers, pairwise, only over lines above them.  Warp w owns the 64-line half-chunks w
+    //    and 2*NW-1-w, two adjacent lines per lane in each, so that every warp sees the same number of (masker, line)
+    //    pairs when maskers are spread evenly over the bins.
+    float acc[4];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        const int l0 = hh ? lb1 : lb0;                    // first of this lane's two lines in half-chunk hh
+        const float2 a2v = *reinterpret_cast<const float2 *>(&sm.P[l0]);
+        float x0 = a2v.x, x1 = a2v.y;
+        const double zd0 = zlined[l0], zd1 = zlined[l0 + 1];
+        const float z0 = (float)zd0, z0l = (float)(zd0 - (double)z0), z1 = (float)zd1, z1l = (float)(zd1 - (double)z1);
+        const int hfirst = l0 & ~63;
+        const int mfull = fs.loudPrefix[ft.kcountU[hfirst]];        // upper skirt starts at or before the half-chunk
+        const int mhi = fs.loudPrefix[ft.kcountU[hfirst + 63]];     // ... at or before its last line
+        int m = 0;
+        for (; m < mfull; m++) {
+            const float4 p = fs.loud[m];
+            const float d0 = (z0 - p.z) + (z0l - p.w), d1 = (z1 - p.z) + (z1l - p.w);
+            x0 += ex2_approx(fmaf(p.y, d0, p.x));
+            x1 += ex2_approx(fmaf(p.y, d1, p.x));
+        }
+        for (; m < mhi; m++) {
+            const float4 p = fs.loud[m];
+            const int eu = fs.loudEU[m];
+            const float d0 = (z0 - p.z) + (z0l - p.w), d1 = (z1 - p.z) + (z1l - p.w);
+            const float t0 = ex2_approx(fmaf(p.y, d0, p.x)), t1 = ex2_approx(fmaf(p.y, d1, p.x));
+            x0 += (l0 >= eu) ? t0 : 0.f;
+            x1 += (l0 + 1 >= eu) ? t1 : 0.f;
+        }
+        acc[2 * hh] = spl_fast(x0 + tb.tiq[l0]);
+        acc[2 * hh + 1] = spl_fast(x1 + tb.tiq[l0 + 1]);
+    }
+    __syncthreads();
+    return make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 template <typename T, int LOGM>
-__global__ void __launch_bounds__((1 << LOGM) / 4)
-k_analysis(const AnalysisArgs<T> a) {
-    using S = AnalysisSmem<T, LOGM>;
+__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? 3 : 1)
+k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
+    using S = AnalysisSmem<T, LOGM, sizeof(T) == 4>;
     using T2 = typename Vec2<T>::type;
     constexpr int M = S::M, N = S::N, NT = S::NT, H = M / 2, NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -183,16 +440,22 @@ k_analysis(const AnalysisArgs<T> a) {
     constexpr int XS = N + 4;
 
     // per-thread constants for its 4 lines i = tid + NT*j
+    // line ownership: fp64 (direct evaluation) thread t owns lines t + NT*j; fp32 (scan-based evaluation): warp w owns the
+    // 64-line half-chunks w and 2*NW-1-w, two adjacent lines per lane in each (see masked_curve_fast step 4).
+    constexpr bool FAST = sizeof(T) == 4;
+    const int lineBase[2] = {64 * warp + 2 * lane, 64 * (2 * NW - 1 - warp) + 2 * lane};
+    auto LI = [&](int j) { return FAST ? lineBase[j >> 1] + (j & 1) : tid + NT * j; };
     T zl[4], zlo[4], tiq[4], mld[4];
     int bnd[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        int i = tid + NT * j;
+        int i = LI(j);
         const double zd = a.tabd.zline[i];
         zl[j] = (T)zd; zlo[j] = (T)(zd - (double)zl[j]);
         tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
     }
 
+    if (tid < 8) sm.P[M + tid] = 0;
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         const int s = (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
@@ -370,25 +633,35 @@ k_analysis(const AnalysisArgs<T> a) {
         __syncthreads();
         // ------------------------------------------------ E. six masked-threshold curves
         T thr[6][4];
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[0]);   // BTHR_L  :540
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[1]);   // BTHR_R  :541
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[2]);    // BTHR_M  :559
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.W[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[3]);    // BTHR_S  :560
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[0], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[4]);   // :561
-        masked_curve<T, LOGM>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[5]);   // :562
+        if constexpr (FAST) {
+            const float2 *srcs[6] = {sm.XF[0], sm.XF[1], sm.W[0], sm.W[1], sm.W[0], sm.W[1]};
+#pragma unroll 1
+            for (int c = 0; c < 6; c++) {
+                const float4 r = masked_curve_fast<LOGM>(sm, srcs[c], c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, a.tabd.zpeak, a.tabd.zline,
+                                                         lineBase[0], lineBase[1]);
+                thr[c][0] = r.x; thr[c][1] = r.y; thr[c][2] = r.z; thr[c][3] = r.w;
+            }
+        } else {
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return sm.XF[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[0]);   // BTHR_L  :540
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return sm.XF[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[1]);   // BTHR_R  :541
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return sm.W[0][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[2]);    // BTHR_M  :559
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return sm.W[1][k]; }, (T)15, zl, zlo, tiq, a.tabd.zpeak, thr[3]);    // BTHR_S  :560
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[0], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[4]);   // :561
+            masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[5]);   // :562
+        }
         // ------------------------------------------------ F. SMR candidates, band maxima, select
         const uint32_t lrms = sm.lrms;
         T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
         T outl[2][4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int i = tid + NT * j;
+            int i = LI(j);
             T xl = sm.Lb[0][i], xr = sm.Lb[1][i];
             T xm = (xl + xr) / 2, xs = (xl - xr) / 2;                                     // psychoac.py:551
-            T sl = spl_of<T>((T)4 * (xl * xl)) - (T)6.02 * (T)osc0;                      // :534
-            T sr = spl_of<T>((T)4 * (xr * xr)) - (T)6.02 * (T)osc1;                      // :535
-            T sM = spl_of<T>((T)4 * (xm * xm)) - (T)6.02 * (T)osc0;                      // :554
-            T sS = spl_of<T>((T)4 * (xs * xs)) - (T)6.02 * (T)osc1;                      // :555
+            T sl = spl_any((T)4 * (xl * xl)) - (T)6.02 * (T)osc0;                        // :534
+            T sr = spl_any((T)4 * (xr * xr)) - (T)6.02 * (T)osc1;                        // :535
+            T sM = spl_any((T)4 * (xm * xm)) - (T)6.02 * (T)osc0;                        // :554
+            T sS = spl_any((T)4 * (xs * xs)) - (T)6.02 * (T)osc1;                        // :555
             T mldM = thr[4][j] * mld[j], mldS = thr[5][j] * mld[j];                      // :582-583
             T thrM = fmax(thr[2][j], fmin(thr[3][j], mldS));                             // :591
             T thrS = fmax(thr[3][j], fmin(thr[2][j], mldM));
@@ -402,14 +675,14 @@ k_analysis(const AnalysisArgs<T> a) {
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int i = tid + NT * j;
+            int i = LI(j);
             a.lines[(w * 2 + 0) * M + i] = outl[0][j];
             a.lines[(w * 2 + 1) * M + i] = outl[1][j];
         }
         if (a.dbg_mdct) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                int i = tid + NT * j;
+                int i = LI(j);
                 a.dbg_mdct[(w * 2 + 0) * M + i] = sm.Lb[0][i];
                 a.dbg_mdct[(w * 2 + 1) * M + i] = sm.Lb[1][i];
             }
@@ -418,7 +691,7 @@ k_analysis(const AnalysisArgs<T> a) {
 #pragma unroll
             for (int c = 0; c < 6; c++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) a.dbg_bthr[(w * 6 + c) * M + tid + NT * j] = thr[c][j];
+                for (int j = 0; j < 4; j++) a.dbg_bthr[(w * 6 + c) * M + LI(j)] = thr[c][j];
         }
         __syncthreads();
         for (int bd = warp; bd < NB; bd += NW) {
@@ -491,7 +764,7 @@ k_calc_smrs(const SmrMonoArgs<T> a) {
     for (int k = tid; k <= M; k += NT) sm.XF[0][k] = rfft_split<T, LOGM>(sm.W[0], k, tb.tw_split);
     __syncthreads();
     T thr[4];
-    masked_curve<T, LOGM>(sm, tb, [&](int k) { return sm.XF[0][k]; }, a.noDrop ? (T)0 : (T)15, zl, zlo, tiq, a.tabd.zpeak, thr);
+    masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return sm.XF[0][k]; }, a.noDrop ? (T)0 : (T)15, zl, zlo, tiq, a.tabd.zpeak, thr);
     T *V = reinterpret_cast<T *>(&sm.W[0][0]);
     const T sc = (T)exp2((double)a.scale);
 #pragma unroll

@@ -49,6 +49,19 @@ struct DevTables {
     T imdct_scale;
 };
 
+// Static geometry + scan weights of the fp32 fast threshold evaluation (analysis.cuh: masked_curve_fast; numpy model
+// in tests/model_analysis.py: Geometry / weighted_suffix_scan / curve_v2).  NT = M/4 "virtual threads" own 4
+// consecutive lines each; chunk = 128 lines = one warp.
+struct FastTables {
+    const short *eL, *eU;        // [M] per bin: last line of its lower skirt (-1: none) / first line of its upper skirt (M: none)
+    const float *xL, *xU;        // [M] per bin: dn * (Bark gap from the skirt origin to that entry line)  (exponent, <= 0)
+    const short *lineTab;        // [6][M] per line: kLa,nL (bins entering the down-scan here), kUa,nU (up-scan), pa,pb (plateau bins)
+    const short *kcountU;        // [M+1] kcountU[i] = number of bins with eU <= i-1 ... see host builder (prefix over lines)
+    const float *sD;             // [13][NT] descending scan weights: wl[3], ww[5], wc, wf[4]
+    const float *sA;             // [10][NT] ascending scan weights: ww[5], wc, wf[4]
+    float omD[16], omA[16];      // per-chunk carry weights
+};
+
 // Encoder scalars derived from PacParams
 struct EncConsts {
     double bitBudget;      // codec.py:223-227

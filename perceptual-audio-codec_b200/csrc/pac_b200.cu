@@ -70,6 +70,7 @@ struct PacCtx {
     std::map<int, TableSet<float>> tf;
     std::map<int, TableSet<double>> td;
     std::map<int, void *> winTables;      // key = kind*65536 + log2N
+    std::map<int, std::pair<FastTables, void *>> fastTables;
     // Huffman
     unsigned long long *lenLut = nullptr;
     uint32_t *codeFlat = nullptr;
@@ -242,6 +243,89 @@ static int build_tables(PacCtx *ctx, int N, TableSet<T> &ts) {
     return PAC_OK;
 }
 
+
+// ------------------------------------------------------------------ fp32 fast-path geometry (tests/model_analysis.py: Geometry)
+struct FastSet { FastTables dev; void *mem = nullptr; };
+
+static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
+    const int M = N / 2, NT = M / 4, NW = NT / 32, fs = ctx->p.sampleRate;
+    std::vector<double> zl(M), zp(M);
+    for (int i = 0; i < M; i++) {
+        zl[i] = h_bark(fs / 2.0 / M * (i + 0.5));
+        zp[i] = h_bark((double)i * (double)(fs / N));
+    }
+    const double dn = -27.0 * (log2(10.0) / 10.0);
+    std::vector<short> eL(M), eU(M), lineTab(6 * M), kcountU(M + 1);
+    std::vector<float> xL(M), xU(M);
+    for (int k = 0; k < M; k++) {
+        int el = -1, eu = M;
+        for (int i = 0; i < M; i++) {
+            double dz = zl[i] - zp[k];
+            if (dz < -0.5) el = i;                         // |dz| > .5 exactly as psychoac.py:116
+            if (dz > 0.5 && eu == M) eu = i;
+        }
+        eL[k] = (short)el; eU[k] = (short)eu;
+        xL[k] = el >= 0 ? (float)(dn * (zp[k] - 0.5 - zl[el])) : 0.f;
+        xU[k] = eu < M ? (float)(dn * (zl[eu] - zp[k] - 0.5)) : 0.f;
+    }
+    for (int k = 1; k < M; k++)
+        if (eL[k] < eL[k - 1] || eU[k] < eU[k - 1]) FAIL(PAC_E_ARG, "Bark tables are not monotone");
+    for (int i = 0; i < M; i++) {
+        int kLa = 0, kLb = 0, kUa = 0, kUb = 0, pa = 0, pb = 0, cu = 0;
+        for (int k = 0; k < M; k++) {
+            if (eL[k] < i) kLa = k + 1;
+            if (eL[k] <= i) kLb = k + 1;
+            if (eU[k] < i) kUa = k + 1;
+            if (eU[k] <= i) { kUb = k + 1; cu = k + 1; }
+            if (eU[k] <= i) pa = k + 1;                    // plateau of line i: eL[k] < i < eU[k]
+            if (eL[k] < i) pb = k + 1;
+        }
+        if (kLb - kLa > 3 || kUb - kUa > 3) FAIL(PAC_E_ARG, "more than 3 bins enter a scan at one line");
+        lineTab[0 * M + i] = (short)kLa; lineTab[1 * M + i] = (short)(kLb - kLa);
+        lineTab[2 * M + i] = (short)kUa; lineTab[3 * M + i] = (short)(kUb - kUa);
+        lineTab[4 * M + i] = (short)pa;  lineTab[5 * M + i] = (short)pb;
+        kcountU[i] = (short)cu;
+    }
+    kcountU[M] = (short)M;
+    auto om = [&](int i, int j) -> float {
+        if (i < 0 || j < 0 || i >= M || j >= M) return 0.f;
+        return (float)exp2(dn * fabs(zl[j] - zl[i]));
+    };
+    std::vector<float> sD(13 * NT), sA(10 * NT);
+    for (int vt = 0; vt < NT; vt++) {
+        const int lane = vt & 31, chunk = vt >> 5, b = 4 * vt;
+        for (int q = 0; q < 3; q++) sD[q * NT + vt] = om(b + q, b + q + 1);
+        for (int s = 0; s < 5; s++) sD[(3 + s) * NT + vt] = (lane + (1 << s) < 32) ? om(b, 4 * (vt + (1 << s))) : 0.f;
+        sD[8 * NT + vt] = (chunk + 1 < NW) ? om(4 * (vt + 1) < M ? 4 * (vt + 1) : M - 1, 128 * (chunk + 1)) : 0.f;
+        if (lane == 31 && chunk + 1 < NW) sD[8 * NT + vt] = 1.f;
+        for (int q = 0; q < 4; q++) sD[(9 + q) * NT + vt] = (b + 4 < M) ? om(b + q, b + 4) : 0.f;
+        for (int s = 0; s < 5; s++) sA[s * NT + vt] = (lane >= (1 << s)) ? om(4 * (vt - (1 << s)) + 3, b + 3) : 0.f;
+        sA[5 * NT + vt] = chunk > 0 ? (lane == 0 ? 1.f : om(128 * chunk - 1, b - 1)) : 0.f;
+        for (int q = 0; q < 4; q++) sA[(6 + q) * NT + vt] = b > 0 ? om(b - 1, b + q) : 0.f;
+    }
+    for (int c = 0; c < 16; c++) {
+        fsd.dev.omD[c] = (c + 1 < NW) ? om(128 * c, 128 * (c + 1)) : 0.f;
+        fsd.dev.omA[c] = (c >= 1 && c < NW) ? om(128 * c - 1, 128 * c + 127) : 0.f;
+    }
+    size_t bytes = (size_t)M * 2 * 2 + (size_t)M * 4 * 2 + (size_t)6 * M * 2 + (size_t)(M + 1) * 2 + 64 + (sD.size() + sA.size()) * 4 + 64;
+    std::vector<unsigned char> host(bytes + 256, 0);
+    size_t o = 0;
+    auto put = [&](const void *src, size_t n) { o = (o + 15) & ~(size_t)15; memcpy(host.data() + o, src, n); size_t r = o; o += n; return r; };
+    size_t o_eL = put(eL.data(), M * 2), o_eU = put(eU.data(), M * 2), o_xL = put(xL.data(), M * 4), o_xU = put(xU.data(), M * 4);
+    size_t o_lt = put(lineTab.data(), 6 * M * 2), o_kc = put(kcountU.data(), (M + 1) * 2);
+    size_t o_sD = put(sD.data(), sD.size() * 4), o_sA = put(sA.data(), sA.size() * 4);
+    CK(cudaMalloc(&fsd.mem, o + 16));
+    CK(cudaMemcpy(fsd.mem, host.data(), o, cudaMemcpyHostToDevice));
+    unsigned char *d = reinterpret_cast<unsigned char *>(fsd.mem);
+    fsd.dev.eL = reinterpret_cast<const short *>(d + o_eL); fsd.dev.eU = reinterpret_cast<const short *>(d + o_eU);
+    fsd.dev.xL = reinterpret_cast<const float *>(d + o_xL); fsd.dev.xU = reinterpret_cast<const float *>(d + o_xU);
+    fsd.dev.lineTab = reinterpret_cast<const short *>(d + o_lt); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
+    fsd.dev.sD = reinterpret_cast<const float *>(d + o_sD); fsd.dev.sA = reinterpret_cast<const float *>(d + o_sA);
+    return PAC_OK;
+}
+
+static int get_fast_tables(PacCtx *ctx, int N, FastTables *out);
+
 template <typename T> static std::map<int, TableSet<T>> &tabmap(PacCtx *ctx);
 template <> std::map<int, TableSet<float>> &tabmap<float>(PacCtx *ctx) { return ctx->tf; }
 template <> std::map<int, TableSet<double>> &tabmap<double>(PacCtx *ctx) { return ctx->td; }
@@ -257,6 +341,18 @@ static int get_tables(PacCtx *ctx, int N, DevTables<T> *out) {
         it = m.emplace(N, ts).first;
     }
     *out = it->second.dev;
+    return PAC_OK;
+}
+
+static int get_fast_tables(PacCtx *ctx, int N, FastTables *out) {
+    auto it = ctx->fastTables.find(N);
+    if (it == ctx->fastTables.end()) {
+        FastSet fsd;
+        int rc = build_fast_tables(ctx, N, fsd);
+        if (rc) return rc;
+        it = ctx->fastTables.emplace(N, std::make_pair(fsd.dev, fsd.mem)).first;
+    }
+    *out = it->second.first;
     return PAC_OK;
 }
 
@@ -402,6 +498,7 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
     for (auto &kv : ctx->winTables) cudaFree(kv.second);
+    for (auto &kv : ctx->fastTables) cudaFree(kv.second.second);
     cudaFree(ctx->lenLut); cudaFree(ctx->codeFlat); cudaFree(ctx->lenFlat);
     cudaFree(ctx->decLut); cudaFree(ctx->trieChild); cudaFree(ctx->trieSym);
     DBuf *bufs[] = {&ctx->w_pcm, &ctx->w_out, &ctx->w_ns, &ctx->w_state, &ctx->w_lines, &ctx->w_smr, &ctx->w_bmax, &ctx->w_osc,
@@ -461,7 +558,7 @@ static void build_header(PacCtx *ctx, int64_t nSamples, uint8_t *h) {
 // ------------------------------------------------------------------ kernel launch helpers
 template <typename T, int LOGM>
 static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
-    size_t smem = sizeof(AnalysisSmem<T, LOGM>);
+    size_t smem = sizeof(AnalysisSmem<T, LOGM, sizeof(T) == 4>);
     static bool configured[2] = {false, false};
     (void)configured;
     CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,6 +581,7 @@ static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
     int rc = get_tables<T>(ctx, ctx->N, &a.tab);
     if (rc) return rc;
     if ((rc = get_tables<double>(ctx, ctx->N, &a.tabd))) return rc;
+    if (sizeof(T) == 4 && (rc = get_fast_tables(ctx, ctx->N, &a.ft))) return rc;
     if (ctx->LOGM == 10) return launch_analysis_t<T, 10>(ctx, a);
     if (ctx->LOGM == 9) return launch_analysis_t<T, 9>(ctx, a);
     FAIL(PAC_E_ARG, "unsupported nMDCTLines");

@@ -14,7 +14,7 @@ import _pacb200  # noqa: E402
 import oracle as orc  # noqa: E402
 
 
-def synth(S, sec, seed=1):
+def synth(S, sec, seed=1, noise_db=None):
     import torch
     n = sec * 44100
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -24,7 +24,8 @@ def synth(S, sec, seed=1):
         f = 50.0 * (320.0 ** torch.rand(S, 1, 1, device="cuda", generator=g))
         amp = 10 ** (-(6 + 24 * torch.rand(S, 1, 2, device="cuda", generator=g)) / 20)
         sig += amp * torch.sin(2 * np.pi * f * t.view(1, n, 1))
-    sig += 10 ** (-(25 + 25 * torch.rand(S, 1, 2, device="cuda", generator=g)) / 20) * torch.randn(S, n, 2, device="cuda", generator=g)
+    nd = (25 + 25 * torch.rand(S, 1, 2, device="cuda", generator=g)) if noise_db is None else torch.full((S, 1, 2), float(noise_db), device="cuda")
+    sig += 10 ** (-nd / 20) * torch.randn(S, n, 2, device="cuda", generator=g)
     return (sig.clamp(-1, 1) * 32767).round().to(torch.int16).contiguous()
 
 
@@ -112,7 +113,42 @@ def corpus():
     print("corpus fp32: %d of %d files byte-identical to fp64; size ratio %.5f" % (same, len(names), sum(map(len, outs32)) / sum(map(len, outs))))
 
 
+def perf_split(S=1024, sec=10):
+    import torch
+    e = _pacb200.Engine(0, "fp32")
+    for tag, nd in (("mixed", None), ("loud noise -25 dBFS", 25), ("quiet noise -50 dBFS", 50), ("no noise", 200)):
+        pcm = synth(S, sec, noise_db=nd)
+        n = pcm.shape[1]
+        cap = e.encode_bound(n)
+        out = torch.empty(S, cap, dtype=torch.uint8, device="cuda")
+        e.encode_batch(pcm, out=out, cap=cap)
+        e.timing(True)
+        e.encode_batch(pcm, out=out, cap=cap)
+        tm = e.timing_get()
+        e.timing(False)
+        nblk = S * e.num_blocks(n)
+        print("%-22s analysis %.1f ns/block  scan %.1f  pack %.1f" % (tag, 1e6 * tm["analysis"][0] / nblk, 1e6 * tm["scan"][0] / nblk, 1e6 * tm["pack"][0] / nblk), flush=True)
+
+
+def perf_one(noise_db, S=296, sec=5):
+    import torch
+    e = _pacb200.Engine(0, "fp32")
+    pcm = synth(S, sec, noise_db=noise_db)
+    n = pcm.shape[1]
+    cap = e.encode_bound(n)
+    out = torch.empty(S, cap, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        e.encode_batch(pcm, out=out, cap=cap)
+    torch.cuda.synchronize()
+    print("one ok")
+
+
 if __name__ == "__main__":
+    if "one" in sys.argv:
+        perf_one(float(sys.argv[sys.argv.index("one") + 1]))
+        sys.exit(0)
+    if "split" in sys.argv:
+        perf_split()
     if "corpus" in sys.argv or len(sys.argv) == 1:
         corpus()
     if "perf" in sys.argv or len(sys.argv) == 1:

@@ -138,3 +138,133 @@ def analysis(T, xl, xr, nLines):
             smr[ch, b] = np.max(v) if n else -96.0
             lines[ch, l0:l0 + n] = ((XM, XS) if lrms[b] else X)[ch][l0:l0 + n]
     return lrms, np.array(osc), np.stack(X), bthr, smr, lines
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# v2 threshold evaluation used by the fp32 fast mode (csrc/analysis.cuh: masked_curve_fast).
+#
+# The reference sums, for every masker, an exp over all 1024 lines (O(maskers x lines)).  The spreading function is
+# piecewise: plateau (|dz| <= .5 Bark), lower skirt (fixed -27 dB/Bark) and upper skirt (-27 + .367 max(P-40, 0)
+# dB/Bark).  Fixed-slope parts are separable, so they become weighted scans over the lines with STATIC weights;
+# only the upper skirts of maskers louder than 40 dB keep a pairwise evaluation, and only over the lines above them.
+# ---------------------------------------------------------------------------------------------------------------
+
+K10 = np.log2(10.0) / 10.0
+
+
+class Geometry:
+    """static line/bin geometry of the v2 evaluation (all from the Bark tables)"""
+
+    def __init__(self, T):
+        M = T.M
+        zl, zp = T.zline, T.zpeak
+        # eL[k]: highest line strictly inside bin k's lower skirt (z_i < zp_k - .5), -1 if none
+        # eU[k]: lowest line strictly inside bin k's upper skirt (z_i > zp_k + .5), M if none
+        self.eL = np.searchsorted(zl, zp - 0.5, side="left") - 1          # z_i <  zp-.5  <=> i <= eL
+        self.eU = np.searchsorted(zl, zp + 0.5, side="right")             # z_i >  zp+.5  <=> i >= eU
+        # careful with the reference's comparisons: plateau is |dz| <= .5 exactly (psychoac.py:116 uses > .5)
+        dz = zl[None, :] - zp[:, None]
+        lower = dz < -0.5
+        upper = dz > 0.5
+        assert all((np.nonzero(lower[k])[0].max(initial=-1) == self.eL[k]) for k in range(M))
+        assert all((np.nonzero(upper[k])[0].min(initial=M) == self.eU[k]) for k in range(M))
+        self.dn = -27.0 * K10
+        # gap from the skirt's origin to its entry line, as exponent factors
+        self.gL = np.where(self.eL >= 0, zp - 0.5 - zl[np.maximum(self.eL, 0)], 0.0)      # >= 0
+        self.gU = np.where(self.eU < M, zl[np.minimum(self.eU, M - 1)] - zp - 0.5, 0.0)   # >= 0
+        # for every line: range of bins whose entry line it is (monotone maps -> contiguous ranges)
+        self.kLa = np.searchsorted(self.eL, np.arange(M), side="left")
+        self.kLb = np.searchsorted(self.eL, np.arange(M), side="right")
+        self.kUa = np.searchsorted(self.eU, np.arange(M), side="left")
+        self.kUb = np.searchsorted(self.eU, np.arange(M), side="right")
+        # plateau of line i: bins k with eL[k] < i < eU[k]  <=> k in [pa_i, pb_i)
+        self.pa = np.searchsorted(self.eU, np.arange(M), side="right")    # first k with eU[k] > i
+        self.pb = np.searchsorted(self.eL, np.arange(M), side="left")     # first k with eL[k] >= i
+        self.M = M
+
+
+def weighted_suffix_scan(U, z, dn, dtype):
+    """L[i] = sum_{j>=i} U[j] 2^{dn (z_j - z_i)} evaluated the way the kernel does: 4 lines per thread, warp
+    Kogge-Stone with static weights, block carry."""
+    M = len(U)
+    w = lambda i, j: dtype(2.0 ** (dn * (z[j] - z[i])))
+    a = np.zeros(M, dtype)
+    nthr = M // 4
+    g = np.zeros(nthr, dtype)
+    for t in range(nthr):
+        b = 4 * t
+        a[b + 3] = U[b + 3]
+        for q in (2, 1, 0):
+            a[b + q] = dtype(U[b + q] + a[b + q + 1] * w(b + q, b + q + 1))
+        g[t] = a[b]
+    nw = nthr // 32
+    for wi in range(nw):
+        base = wi * 32
+        for s in (1, 2, 4, 8, 16):
+            old = g.copy()
+            for l in range(32):
+                if l + s < 32:
+                    t = base + l
+                    g[t] = dtype(old[t] + old[t + s] * w(4 * t, 4 * (t + s)))
+    tot = np.array([g[wi * 32] for wi in range(nw)], dtype)
+    out = np.zeros(M, dtype)
+    for wi in range(nw):
+        C = dtype(0)
+        for w2 in range(nw - 1, wi, -1):
+            nxt = 128 * (w2 + 1)
+            C = dtype(tot[w2] + C * (w(128 * w2, nxt) if nxt < M else dtype(0)))
+        for l in range(32):
+            t = wi * 32 + l
+            nb = 4 * (t + 1)
+            inc = dtype(g[t + 1]) if l < 31 else dtype(0)
+            if wi < nw - 1:
+                inc = dtype(inc + C * w(nb, 128 * (wi + 1))) if nb <= 128 * (wi + 1) else inc
+            for q in range(4):
+                i = 4 * t + q
+                out[i] = dtype(a[i] + (inc * w(i, nb) if nb < M else dtype(0)))
+    return out
+
+
+def curve_v2(T, G, F, drop, dtype=np.float32, stats=None):
+    M, N = T.M, T.N
+    P = (F.real.astype(dtype) ** 2 + F.imag.astype(dtype) ** 2)[:M]
+    k = np.arange(1, M - 1)
+    pk = k[(P[k] > P[k - 1]) & (P[k] > P[k + 1]) & (P[k] > dtype(1e-6))]
+    A = np.zeros(M, dtype); V = np.zeros(M, dtype); W = np.zeros(M, dtype)
+    loud = []
+    cn = dtype(8.0 / 3.0 * 4.0 / N ** 2)
+    for kk in pk:
+        s = dtype(0) if kk < 3 else np.sum(P[kk - 3:min(kk + 3, M)], dtype=dtype)
+        Pm = dtype(max(96 + 10 * np.log10(max(dtype(cn * s), dtype(10 ** -12.6))), -30.0))
+        c0 = dtype((Pm - dtype(drop) - dtype(96)) * dtype(K10))
+        A[kk] = dtype(2.0 ** c0)
+        if G.eL[kk] >= 0:
+            V[kk] = dtype(2.0 ** dtype(c0 + dtype(G.dn) * dtype(G.gL[kk])))
+        lev = dtype(0.367) * max(Pm - dtype(40), dtype(0))
+        if G.eU[kk] < M:
+            if lev > 0:
+                loud.append((kk, c0, dtype((lev - dtype(27)) * dtype(K10))))
+            else:
+                W[kk] = dtype(2.0 ** dtype(c0 + dtype(G.dn) * dtype(G.gU[kk])))
+    # injections gathered per line (deterministic order)
+    UL = np.array([np.sum(V[G.kLa[i]:G.kLb[i]], dtype=dtype) for i in range(M)], dtype)
+    UU = np.array([np.sum(W[G.kUa[i]:G.kUb[i]], dtype=dtype) for i in range(M)], dtype)
+    low = weighted_suffix_scan(UL, T.zline, G.dn, dtype)
+    upq = weighted_suffix_scan(UU[::-1].copy(), -T.zline[::-1], G.dn, dtype)[::-1]
+    plat = np.array([np.sum(A[G.pa[i]:G.pb[i]], dtype=dtype) for i in range(M)], dtype)
+    acc = (low + plat + upq).astype(dtype)
+    # loud upper skirts: pairwise over the lines above the masker
+    zl = T.zline
+    npairs = 0
+    for kk, c0, up in loud:
+        i0 = G.eU[kk]
+        dz = (zl[i0:] - T.zpeak[kk] - 0.5)           # formed from hi+lo pairs in the kernel: exact to ~1e-9 Bark
+        e = (c0 + up * dz.astype(dtype)).astype(dtype)
+        acc[i0:] += (2.0 ** e.astype(np.float64)).astype(dtype)
+        npairs += M - i0
+    if stats is not None:
+        stats["peaks"] = stats.get("peaks", 0) + len(pk)
+        stats["loud"] = stats.get("loud", 0) + len(loud)
+        stats["pairs"] = stats.get("pairs", 0) + npairs
+    tot = (acc + T.tiq.astype(dtype)).astype(dtype)
+    return np.maximum(dtype(96) + dtype(10) * np.log10(np.maximum(tot, dtype(10 ** -12.6))).astype(dtype), dtype(-30))
