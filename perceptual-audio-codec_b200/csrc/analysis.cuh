@@ -255,10 +255,11 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
                 const float lev = 0.367f * fmaxf(pmv - 40.0f, 0.f);
                 Av = ex2_approx(c0);
                 const int el = ft.eL[k], eu = ft.eU[k];
-                if (el >= 0) Vv = ex2_approx(c0 + ft.xL[k]);
+                const float4 bt = ft.binTab[k];
+                if (el >= 0) Vv = ex2_approx(c0 + bt.x);
                 if (eu < M) {
                     if (lev > 0.f) { loudf |= 1u << q; ups[q] = (lev - 27.0f) * K; c0s[q] = c0; }
-                    else Wv = ex2_approx(c0 + ft.xU[k]);
+                    else Wv = ex2_approx(c0 + bt.y);
                 }
             }
             fs.Ah[k] = Av; fs.V[k] = Vv; fs.Wq[k] = Wv;
@@ -278,9 +279,8 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
         fs.loudPrefix[k0 + q] = (unsigned short)offs;
         if (loudf & (1u << q)) {
             const int k = k0 + q;
-            const double zp = zpeakd[k];
-            const float zph = (float)zp;
-            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], zph, (float)(zp - (double)zph));
+            const float4 bt = ft.binTab[k];
+            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], bt.z, bt.w);
             fs.loudEU[offs] = ft.eU[k];
             offs++;
         }
@@ -300,44 +300,27 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     __syncthreads();
     // 3. per-line gathers (deterministic order) + plateau + the two scans; thread t owns lines 4t .. 4t+3
     {
-        float uD[4], uA[4], pl[4];
-        int pa[4], pb[4];
+        float uD[4], uA[4], pl[4] = {0.f, 0.f, 0.f, 0.f};
         const short *lt = ft.lineTab + 4 * tid;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int kLa = lt[0 * M + q], nL = lt[1 * M + q], kUa = lt[2 * M + q], nU = lt[3 * M + q];
             uD[q] = (nL > 0 ? fs.V[kLa] : 0.f) + (nL > 1 ? fs.V[kLa + 1] : 0.f) + (nL > 2 ? fs.V[kLa + 2] : 0.f);
             uA[q] = (nU > 0 ? fs.Wq[kUa] : 0.f) + (nU > 1 ? fs.Wq[kUa + 1] : 0.f) + (nU > 2 ? fs.Wq[kUa + 2] : 0.f);
-            pa[q] = lt[4 * M + q];
-            pb[q] = lt[5 * M + q];
         }
-        // plateau: the 4 windows [pa_q, pb_q) slide monotonically: sum their common core [pa_3, pb_0) once through the
-        // block-sum pyramid (1, 4, 16, 64 bins) and add each line's few extra bins at either end
+        // plateau: sum over the (static) window of bins within +-.5 Bark of each line.  The host decomposed the four
+        // windows of this thread into entries of the block-sum pyramid (1, 4, 16, 64 bins), each tagged with the lines
+        // it belongs to; the walk is branch-free and as long as the warp's longest list.
         {
-            float core = 0.f;
-            int k = pa[3];
-            const int ke = pb[0];
-            const bool hascore = k < ke;
-            if (hascore) {
-                while (k < ke && (k & 3)) core += fs.Ah[k++];
-                while (k + 4 <= ke && (k & 15)) { core += fs.Ah[O4 + (k >> 2)]; k += 4; }
-                while (k + 16 <= ke && (k & 63)) { core += fs.Ah[O16 + (k >> 4)]; k += 16; }
-                while (k + 64 <= ke) { core += fs.Ah[O64 + (k >> 6)]; k += 64; }
-                while (k + 16 <= ke) { core += fs.Ah[O16 + (k >> 4)]; k += 16; }
-                while (k + 4 <= ke) { core += fs.Ah[O4 + (k >> 2)]; k += 4; }
-                while (k < ke) core += fs.Ah[k++];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                float s = 0.f;
-                if (hascore) {
-                    for (int kk = pa[q]; kk < pa[3]; kk++) s += fs.Ah[kk];
-                    s += core;
-                    for (int kk = pb[0]; kk < pb[q]; kk++) s += fs.Ah[kk];
-                } else {
-                    for (int kk = pa[q]; kk < pb[q]; kk++) s += fs.Ah[kk];
-                }
-                pl[q] = s;
+            const unsigned *pe = ft.platList + tid;
+            const int n = ft.platCnt[warp];
+            for (int e = 0; e < n; e++) {
+                const unsigned ent = pe[e * NT];
+                const float v = fs.Ah[ent & 0xffffu];
+                pl[0] += (ent & (1u << 16)) ? v : 0.f;
+                pl[1] += (ent & (1u << 17)) ? v : 0.f;
+                pl[2] += (ent & (1u << 18)) ? v : 0.f;
+                pl[3] += (ent & (1u << 19)) ? v : 0.f;
             }
         }
         // descending scan: low[i] = sum_{j >= i} uD[j] 2^{dn (z_j - z_i)}
@@ -398,8 +381,8 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
         const int l0 = hh ? lb1 : lb0;                    // first of this lane's two lines in half-chunk hh
         const float2 a2v = *reinterpret_cast<const float2 *>(&sm.P[l0]);
         float x0 = a2v.x, x1 = a2v.y;
-        const double zd0 = zlined[l0], zd1 = zlined[l0 + 1];
-        const float z0 = (float)zd0, z0l = (float)(zd0 - (double)z0), z1 = (float)zd1, z1l = (float)(zd1 - (double)z1);
+        const float4 zz = *reinterpret_cast<const float4 *>(&ft.lineZ[l0]);      // l0 is even: (z0_hi, z0_lo, z1_hi, z1_lo)
+        const float z0 = zz.x, z0l = zz.y, z1 = zz.z, z1l = zz.w;
         const int hfirst = l0 & ~63;
         const int mfull = fs.loudPrefix[ft.kcountU[hfirst]];        // upper skirt starts at or before the half-chunk
         const int mhi = fs.loudPrefix[ft.kcountU[hfirst + 63]];     // ... at or before its last line
@@ -456,6 +439,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     }
 
     if (tid < 8) sm.P[M + tid] = 0;
+    if constexpr (sizeof(T) == 4) { if (tid < 4) sm.fs.Ah[M + M / 4 + M / 16 + M / 64 + tid] = 0.f; }
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         const int s = (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
@@ -557,8 +541,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                     int c = ch ? (pv >> 16) : (int)(short)(pv & 0xffff);
                     int code = c < 0 ? -c : c;
                     if (code & 32768) code -= 32768;
-                    v = 2.0 * (double)code / 65535.0;
-                    if (c < 0) v = -v;
+                    v = (double)(c < 0 ? -code : code) * (2.0 / 65535.0);      // fp32 mode: 1 ulp of a double is irrelevant
                 } else v = a.blocks[w * 2 * N + ch * N + n];
                 return v * td.sinw[n];
             };

@@ -57,6 +57,10 @@ struct FastTables {
     const float *xL, *xU;        // [M] per bin: dn * (Bark gap from the skirt origin to that entry line)  (exponent, <= 0)
     const short *lineTab;        // [6][M] per line: kLa,nL (bins entering the down-scan here), kUa,nU (up-scan), pa,pb (plateau bins)
     const short *kcountU;        // [M+1] kcountU[i] = number of bins with eU <= i-1 ... see host builder (prefix over lines)
+    const float4 *binTab;        // [M] per bin: (xL, xU, zpeak_hi, zpeak_lo)
+    const float2 *lineZ;         // [M] per line: Bark position as hi + lo floats
+    const unsigned *platList;    // [platLen][NT] per scan thread: pyramid entries (index | line mask << 16) of its 4 plateau sums
+    const unsigned char *platCnt;// [NT/32] entries to walk per warp (lists are padded to the warp's longest with no-op entries)
     const float *sD;             // [13][NT] descending scan weights: wl[3], ww[5], wc, wf[4]
     const float *sA;             // [10][NT] ascending scan weights: ww[5], wc, wf[4]
     float omD[16], omA[16];      // per-chunk carry weights
