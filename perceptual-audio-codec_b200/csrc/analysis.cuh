@@ -45,7 +45,8 @@ struct AnalysisArgs {
 template <int LOGM>
 struct FastSmem {
     static constexpr int M = 1 << LOGM;
-    float Ah[M + M / 4 + M / 16 + M / 64 + 4];   // plateau intensity per bin, then its 4-, 16- and 64-bin block sums
+    double Sp[M + 2];             // exclusive prefix sums (in double) of the plateau intensities A_k over the bins
+    double wtot[16];
     float V[M], Wq[M];            // dense per bin: down-scan injection, up-scan injection (quiet maskers)
     float4 loud[M / 2];           // maskers louder than 40 dB: (c0 - up/2, up, zk_hi, zk_lo)
     short loudEU[M / 2];          // their first upper-skirt line
@@ -214,7 +215,6 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
                                                  const DevTables<float> *tbp, const FastTables *ftp, const double *zpeakd,
                                                  const double *zlined, int lb0, int lb1) {
     constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
-    constexpr int O4 = M, O16 = M + M / 4, O64 = M + M / 4 + M / 16;
     const DevTables<float> &tb = *tbp;
     const FastTables &ft = *ftp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,12 +234,11 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     // 2. findpeaks on this thread's 4 bins; dense A / V / Wq; ordered list of the loud maskers
     const int k0 = 4 * tid;
     unsigned loudf = 0;
-    float c0s[4], ups[4];
+    float c0s[4], ups[4], Aq[4];
     {
         float pw[10];                                 // P[k0-3 .. k0+6]; P[M..M+7] are kept zero
 #pragma unroll
         for (int q = 0; q < 10; q++) { int kk = k0 - 3 + q; pw[q] = kk >= 0 ? sm.P[kk] : 0.f; }
-        float a4 = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int k = k0 + q;
@@ -262,18 +261,28 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
                     else Wv = ex2_approx(c0 + bt.y);
                 }
             }
-            fs.Ah[k] = Av; fs.V[k] = Vv; fs.Wq[k] = Wv;
-            a4 += Av;
+            fs.V[k] = Vv; fs.Wq[k] = Wv;
+            Aq[q] = Av;
         }
-        fs.Ah[O4 + tid] = a4;
     }
     int nl = __popc(loudf), incl = nl;
+    // plateau intensities: block-wide prefix sum in DOUBLE (range sums become differences of prefixes; in fp32 the
+    // difference would carry the rounding residue of every louder masker below the window)
+    const double A0 = (double)Aq[0], A1 = A0 + (double)Aq[1], A2 = A1 + (double)Aq[2], A3 = A2 + (double)Aq[3];
+    double dincl = A3;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) sm.wsum[warp] = incl;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        double dv = __shfl_up_sync(0xffffffffu, dincl, o);
+        if (lane >= o) { incl += v; dincl += dv; }
+    }
+    if (lane == 31) { sm.wsum[warp] = incl; fs.wtot[warp] = dincl; }
     __syncthreads();
     int offs = incl - nl;
-    for (int i = 0; i < warp; i++) offs += sm.wsum[i];
+    double dbase = dincl - A3;
+    for (int i = 0; i < warp; i++) { offs += sm.wsum[i]; dbase += fs.wtot[i]; }
+    fs.Sp[k0] = dbase; fs.Sp[k0 + 1] = dbase + A0; fs.Sp[k0 + 2] = dbase + A1; fs.Sp[k0 + 3] = dbase + A2;
+    if (tid == NT - 1) fs.Sp[M] = dbase + A3;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         fs.loudPrefix[k0 + q] = (unsigned short)offs;
@@ -286,42 +295,20 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
         }
     }
     if (tid == NT - 1) { fs.loudPrefix[M] = (unsigned short)offs; fs.loudPrefix[M + 1] = (unsigned short)offs; }
-    if (tid < M / 16) {
-        const float *p4 = fs.Ah + O4 + 4 * tid;
-        fs.Ah[O16 + tid] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
-    }
-    if (tid >= NT - M / 64) {
-        const float *p4 = fs.Ah + O4 + 16 * (tid - (NT - M / 64));
-        float s = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; q++) s += p4[q];
-        fs.Ah[O64 + tid - (NT - M / 64)] = s;
-    }
     __syncthreads();
     // 3. per-line gathers (deterministic order) + plateau + the two scans; thread t owns lines 4t .. 4t+3
     {
-        float uD[4], uA[4], pl[4] = {0.f, 0.f, 0.f, 0.f};
-        const short *lt = ft.lineTab + 4 * tid;
+        float uD[4], uA[4], pl[4];
+        const uint4 lg = ft.lineGather[tid];              // per line: kLa | nL << 10 | kUa << 12 | nU << 22
+        const uint4 lp = ft.linePlat[tid];                // per line: pa | pb << 16
+        const unsigned lgq[4] = {lg.x, lg.y, lg.z, lg.w}, lpq[4] = {lp.x, lp.y, lp.z, lp.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int kLa = lt[0 * M + q], nL = lt[1 * M + q], kUa = lt[2 * M + q], nU = lt[3 * M + q];
+            const int kLa = lgq[q] & 1023, nL = (lgq[q] >> 10) & 3, kUa = (lgq[q] >> 12) & 1023, nU = (lgq[q] >> 22) & 3;
             uD[q] = (nL > 0 ? fs.V[kLa] : 0.f) + (nL > 1 ? fs.V[kLa + 1] : 0.f) + (nL > 2 ? fs.V[kLa + 2] : 0.f);
             uA[q] = (nU > 0 ? fs.Wq[kUa] : 0.f) + (nU > 1 ? fs.Wq[kUa + 1] : 0.f) + (nU > 2 ? fs.Wq[kUa + 2] : 0.f);
-        }
-        // plateau: sum over the (static) window of bins within +-.5 Bark of each line.  The host decomposed the four
-        // windows of this thread into entries of the block-sum pyramid (1, 4, 16, 64 bins), each tagged with the lines
-        // it belongs to; the walk is branch-free and as long as the warp's longest list.
-        {
-            const unsigned *pe = ft.platList + tid;
-            const int n = ft.platCnt[warp];
-            for (int e = 0; e < n; e++) {
-                const unsigned ent = pe[e * NT];
-                const float v = fs.Ah[ent & 0xffffu];
-                pl[0] += (ent & (1u << 16)) ? v : 0.f;
-                pl[1] += (ent & (1u << 17)) ? v : 0.f;
-                pl[2] += (ent & (1u << 18)) ? v : 0.f;
-                pl[3] += (ent & (1u << 19)) ? v : 0.f;
-            }
+            // plateau: bins within +-.5 Bark of the line = static window [pa, pb)
+            pl[q] = (float)(fs.Sp[lpq[q] >> 16] - fs.Sp[lpq[q] & 0xffffu]);
         }
         // descending scan: low[i] = sum_{j >= i} uD[j] 2^{dn (z_j - z_i)}
         const float *w = ft.sD + tid;
@@ -439,7 +426,6 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     }
 
     if (tid < 8) sm.P[M + tid] = 0;
-    if constexpr (sizeof(T) == 4) { if (tid < 4) sm.fs.Ah[M + M / 4 + M / 16 + M / 64 + tid] = 0.f; }
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         const int s = (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);

@@ -59,8 +59,8 @@ struct FastTables {
     const short *kcountU;        // [M+1] kcountU[i] = number of bins with eU <= i-1 ... see host builder (prefix over lines)
     const float4 *binTab;        // [M] per bin: (xL, xU, zpeak_hi, zpeak_lo)
     const float2 *lineZ;         // [M] per line: Bark position as hi + lo floats
-    const unsigned *platList;    // [platLen][NT] per scan thread: pyramid entries (index | line mask << 16) of its 4 plateau sums
-    const unsigned char *platCnt;// [NT/32] entries to walk per warp (lists are padded to the warp's longest with no-op entries)
+    const uint4 *lineGather;     // [NT] per scan thread, per line: kLa | nL << 10 | kUa << 12 | nU << 22
+    const uint4 *linePlat;       // [NT] per scan thread, per line: pa | pb << 16 (plateau bin window)
     const float *sD;             // [13][NT] descending scan weights: wl[3], ww[5], wc, wf[4]
     const float *sA;             // [10][NT] ascending scan weights: ww[5], wc, wf[4]
     float omD[16], omA[16];      // per-chunk carry weights

@@ -288,43 +288,13 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         kcountU[i] = (short)cu;
     }
     kcountU[M] = (short)M;
-    // plateau decomposition lists (see masked_curve_fast step 3)
-    const int O4 = M, O16 = M + M / 4, O64 = M + M / 4 + M / 16, ZERO = M + M / 4 + M / 16 + M / 64;
-    std::vector<std::vector<unsigned>> plist(NT);
-    auto decompose = [&](int lo, int hi, unsigned mask, std::vector<unsigned> &out) {
-        int k = lo;
-        while (k < hi && (k & 3)) out.push_back((unsigned)k++ | mask);
-        while (k + 4 <= hi && (k & 15)) { out.push_back((unsigned)(O4 + (k >> 2)) | mask); k += 4; }
-        while (k + 16 <= hi && (k & 63)) { out.push_back((unsigned)(O16 + (k >> 4)) | mask); k += 16; }
-        while (k + 64 <= hi) { out.push_back((unsigned)(O64 + (k >> 6)) | mask); k += 64; }
-        while (k + 16 <= hi) { out.push_back((unsigned)(O16 + (k >> 4)) | mask); k += 16; }
-        while (k + 4 <= hi) { out.push_back((unsigned)(O4 + (k >> 2)) | mask); k += 4; }
-        while (k < hi) out.push_back((unsigned)k++ | mask);
-    };
-    size_t platLen = 0;
-    for (int t = 0; t < NT; t++) {
-        int pa[4], pb[4];
-        for (int q = 0; q < 4; q++) { pa[q] = lineTab[4 * M + 4 * t + q]; pb[q] = lineTab[5 * M + 4 * t + q]; }
-        // the bins of [pa_0, pb_3) split at every window edge; each segment belongs to a fixed subset of the 4 lines
-        std::vector<int> cuts;
-        for (int q = 0; q < 4; q++) { cuts.push_back(pa[q]); cuts.push_back(pb[q]); }
-        std::sort(cuts.begin(), cuts.end());
-        for (size_t c = 0; c + 1 < cuts.size(); c++) {
-            int lo = cuts[c], hi = cuts[c + 1];
-            if (lo >= hi) continue;
-            unsigned mask = 0;
-            for (int q = 0; q < 4; q++) if (pa[q] <= lo && hi <= pb[q]) mask |= 1u << (16 + q);
-            if (mask) decompose(lo, hi, mask, plist[t]);
-        }
-        if (plist[t].size() > platLen) platLen = plist[t].size();
+    std::vector<unsigned> lineGather(M), linePlat(M);
+    for (int i = 0; i < M; i++) {
+        lineGather[i] = (unsigned)lineTab[0 * M + i] | ((unsigned)lineTab[1 * M + i] << 10) | ((unsigned)lineTab[2 * M + i] << 12) |
+                        ((unsigned)lineTab[3 * M + i] << 22);
+        linePlat[i] = (unsigned)lineTab[4 * M + i] | ((unsigned)lineTab[5 * M + i] << 16);
     }
-    if (platLen > 255) FAIL(PAC_E_ARG, "plateau list too long");
-    std::vector<unsigned> platList(platLen * NT, (unsigned)ZERO);
-    std::vector<unsigned char> platCnt(NW, 0);
-    for (int t = 0; t < NT; t++) {
-        for (size_t e = 0; e < plist[t].size(); e++) platList[e * NT + t] = plist[t][e];
-        if (plist[t].size() > platCnt[t / 32]) platCnt[t / 32] = (unsigned char)plist[t].size();
-    }
+    if (M > 1024) FAIL(PAC_E_ARG, "fast tables pack bin indices in 10 bits");
     std::vector<float> binTab(4 * M), lineZ(2 * M);
     for (int k = 0; k < M; k++) {
         float zh = (float)zp[k];
@@ -353,7 +323,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         fsd.dev.omA[c] = (c >= 1 && c < NW) ? om(128 * c - 1, 128 * c + 127) : 0.f;
     }
     size_t bytes = (size_t)M * 2 * 2 + (size_t)M * 4 * 2 + (size_t)6 * M * 2 + (size_t)(M + 1) * 2 + 64 + (sD.size() + sA.size()) * 4 + 64 +
-                   binTab.size() * 4 + lineZ.size() * 4 + platList.size() * 4 + platCnt.size() + 256;
+                   binTab.size() * 4 + lineZ.size() * 4 + (lineGather.size() + linePlat.size()) * 4 + 256;
     std::vector<unsigned char> host(bytes + 256, 0);
     size_t o = 0;
     auto put = [&](const void *src, size_t n) { o = (o + 15) & ~(size_t)15; memcpy(host.data() + o, src, n); size_t r = o; o += n; return r; };
@@ -361,7 +331,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
     size_t o_lt = put(lineTab.data(), 6 * M * 2), o_kc = put(kcountU.data(), (M + 1) * 2);
     size_t o_sD = put(sD.data(), sD.size() * 4), o_sA = put(sA.data(), sA.size() * 4);
     size_t o_bt = put(binTab.data(), binTab.size() * 4), o_lz = put(lineZ.data(), lineZ.size() * 4);
-    size_t o_pl = put(platList.data(), platList.size() * 4), o_pc = put(platCnt.data(), platCnt.size());
+    size_t o_lg = put(lineGather.data(), lineGather.size() * 4), o_lp = put(linePlat.data(), linePlat.size() * 4);
     CK(cudaMalloc(&fsd.mem, o + 16));
     CK(cudaMemcpy(fsd.mem, host.data(), o, cudaMemcpyHostToDevice));
     unsigned char *d = reinterpret_cast<unsigned char *>(fsd.mem);
@@ -370,7 +340,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
     fsd.dev.lineTab = reinterpret_cast<const short *>(d + o_lt); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
     fsd.dev.sD = reinterpret_cast<const float *>(d + o_sD); fsd.dev.sA = reinterpret_cast<const float *>(d + o_sA);
     fsd.dev.binTab = reinterpret_cast<const float4 *>(d + o_bt); fsd.dev.lineZ = reinterpret_cast<const float2 *>(d + o_lz);
-    fsd.dev.platList = reinterpret_cast<const unsigned *>(d + o_pl); fsd.dev.platCnt = reinterpret_cast<const unsigned char *>(d + o_pc);
+    fsd.dev.lineGather = reinterpret_cast<const uint4 *>(d + o_lg); fsd.dev.linePlat = reinterpret_cast<const uint4 *>(d + o_lp);
     return PAC_OK;
 }
 
