@@ -461,18 +461,28 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         }
         __syncthreads();
         // ------------------------------------------------ B. raw FFTs -> LRMS decision (codec.py:96-102)
+        // fp64: raw FFTs of L, R in W.  fp32: the raw FFTs run IN PLACE in XF and, in the same batch of four, the FFTs of the
+        // sine*Hann windowed channels in W (the fp32 MDCT re-reads the samples from global memory, so x is not needed later).
+        T2(*RAW)[M + 2] = FAST ? sm.XF : sm.W;
         for (int e = tid; e < 2 * M; e += NT) {
             int ch = e / M, m = e - ch * M;
-            sm.W[ch][m] = sm.XF[ch][m];                   // (x[2m], x[2m+1])
+            const T2 x2 = sm.XF[ch][m];                   // (x[2m], x[2m+1])
+            if constexpr (FAST) {
+                const T2 s2 = reinterpret_cast<const T2 *>(tb.sinw)[m], h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
+                sm.W[ch][m] = mk2<T>((x2.x * s2.x) * h2.x, (x2.y * s2.y) * h2.y);      // window.py:37 then psychoac.py:428
+            } else {
+                sm.W[ch][m] = x2;
+            }
         }
         if (tid == 0) sm.lrms = 0;
         __syncthreads();
-        fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+        if constexpr (FAST) fft_dif<T, LOGM, NT>(&sm.XF[0][0], 4, M + 2, tb.tw, 1);
+        else fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
         for (int bd = warp; bd < NB; bd += NW) {
             T dr = 0, di = 0, sr = 0, si = 0;
             for (int k = a.bands.lo[bd] + lane; k < a.bands.lo[bd + 1]; k += 32) {
-                T2 l = rfft_split<T, LOGM>(sm.W[0], k, tb.tw_split);
-                T2 r = rfft_split<T, LOGM>(sm.W[1], k, tb.tw_split);
+                T2 l = rfft_split<T, LOGM>(RAW[0], k, tb.tw_split);
+                T2 r = rfft_split<T, LOGM>(RAW[1], k, tb.tw_split);
                 T l2r = l.x * l.x - l.y * l.y, l2i = l.x * l.y + l.y * l.x;
                 T r2r = r.x * r.x - r.y * r.y, r2i = r.x * r.y + r.y * r.x;
                 dr += l2r - r2r; di += l2i - r2i;
@@ -485,12 +495,21 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             }
         }
         __syncthreads();
-        // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
-        for (int e = tid; e < 2 * N; e += NT) {
-            int ch = e / N, n = e - ch * N;
-            xt[ch * XS + n] *= tb.sinw[n];
+        if constexpr (FAST) {
+            for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M, into XF (the raw spectra are dead)
+                int ch = e / (M + 1), k = e - ch * (M + 1);
+                sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
+        if constexpr (!FAST) {
+            for (int e = tid; e < 2 * N; e += NT) {
+                int ch = e / N, n = e - ch * N;
+                xt[ch * XS + n] *= tb.sinw[n];
+            }
+            __syncthreads();
+        }
         T mx[2] = {0, 0};
         if constexpr (sizeof(T) == 8) {
             for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
@@ -568,20 +587,24 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             int ch = e / M, i = e - ch * M;
             sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
         }
-        // ------------------------------------------------ D. Hann on the sine-windowed data (psychoac.py:428) + FFT
-        for (int e = tid; e < 2 * M; e += NT) {
-            int ch = e / M, m = e - ch * M;
-            T2 x2 = sm.XF[ch][m];
-            const T2 h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
-            sm.W[ch][m] = mk2<T>(x2.x * h2.x, x2.y * h2.y);
+        if constexpr (!FAST) {
+            // ------------------------------------------------ D. Hann on the sine-windowed data (psychoac.py:428) + FFT
+            for (int e = tid; e < 2 * M; e += NT) {
+                int ch = e / M, m = e - ch * M;
+                T2 x2 = sm.XF[ch][m];
+                const T2 h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
+                sm.W[ch][m] = mk2<T>(x2.x * h2.x, x2.y * h2.y);
+            }
+            __syncthreads();
+            fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+            for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M
+                int ch = e / (M + 1), k = e - ch * (M + 1);
+                sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
+            }
+            __syncthreads();
+        } else {
+            __syncthreads();
         }
-        __syncthreads();
-        fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
-        for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M
-            int ch = e / (M + 1), k = e - ch * (M + 1);
-            sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
-        }
-        __syncthreads();
         // F2_M, F2_S = Hann-taps of (F1_L +- F1_R)/2   (psychoac.py:549 then :428 again)
         const T2 hw = tb.hann_w, hwc = cconj(tb.hann_w);
         for (int e = tid; e < 2 * (M + 1); e += NT) {
