@@ -74,6 +74,7 @@ struct PacCtx {
     std::map<int, std::pair<FastTables, void *>> fastTables;
     // Huffman
     unsigned long long *lenLut = nullptr;
+    ulonglong4 *lenLut4 = nullptr;
     uint32_t *codeFlat = nullptr;
     uint8_t *lenFlat = nullptr;
     uint32_t *decLut = nullptr;
@@ -397,6 +398,18 @@ static int build_huffman(PacCtx *ctx, const PacHuffTables *h) {
             if (l > 31) FAIL(PAC_E_ARG, "Huffman code longer than 31 bits");
             lut[v] |= (unsigned long long)l << (5 * t);
         }
+    {   // packed-slot variant used by the scan kernel
+        std::vector<unsigned long long> l4((size_t)(kLenLutSize + 1) * 4, 0ull);
+        for (int v = 0; v <= kLenLutSize; v++)
+            for (int t = 0; t < kNTables; t++) {
+                unsigned l = (v < kLenLutSize && v < h->nkeys[t]) ? h->len[h->off[t] + v] : 0;
+                int w = t < 5 ? 0 : 1, sh = 12 * (t % 5);
+                if (l) l4[(size_t)v * 4 + w] |= (unsigned long long)l << sh;
+                else { l4[(size_t)v * 4 + w] |= (unsigned long long)h->esc_len[t] << sh; l4[(size_t)v * 4 + 2 + w] |= 1ull << sh; }
+            }
+        CK(cudaMalloc(&ctx->lenLut4, l4.size() * 8));
+        CK(cudaMemcpy(ctx->lenLut4, l4.data(), l4.size() * 8, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&ctx->lenLut, lut.size() * 8));
     CK(cudaMemcpy(ctx->lenLut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&ctx->codeFlat, (size_t)total * 4));
@@ -519,7 +532,7 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
     for (auto &kv : ctx->winTables) cudaFree(kv.second);
     for (auto &kv : ctx->fastTables) cudaFree(kv.second.second);
-    cudaFree(ctx->lenLut); cudaFree(ctx->codeFlat); cudaFree(ctx->lenFlat);
+    cudaFree(ctx->lenLut); cudaFree(ctx->lenLut4); cudaFree(ctx->codeFlat); cudaFree(ctx->lenFlat);
     cudaFree(ctx->decLut); cudaFree(ctx->trieChild); cudaFree(ctx->trieSym);
     DBuf *bufs[] = {&ctx->w_pcm, &ctx->w_out, &ctx->w_ns, &ctx->w_state, &ctx->w_lines, &ctx->w_smr, &ctx->w_bmax, &ctx->w_osc,
                     &ctx->w_lrms, &ctx->w_ba, &ctx->w_sf, &ctx->w_tid, &ctx->w_nby, &ctx->w_coff, &ctx->w_trE, &ctx->w_trD,
@@ -609,7 +622,13 @@ static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
 
 template <typename T>
 static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
-    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.lenLut = ctx->lenLut;
+    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.lenLut = ctx->lenLut; a.lenLut4 = ctx->lenLut4;
+    {
+        DevTables<T> tb;
+        int rc = get_tables<T>(ctx, ctx->N, &tb);
+        if (rc) return rc;
+        a.band_of_line = tb.band_of_line;
+    }
     constexpr int WARPS = 4;
     { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, ctx->stream>>>(a); }
     ctx->launches++;

@@ -31,11 +31,52 @@ struct ScanArgs {
     long long *chunkOff;           // [nwork][2] offset of the chunk's length prefix in the stream image
     long long *trExtra, *trDeposit;// [nwork] optional traces of the state after each block
     const unsigned long long *lenLut;   // [kLenLutSize] 10 x 5-bit code lengths per magnitude (0 = escape)
+    const ulonglong4 *lenLut4;          // [kLenLutSize+1] per magnitude: code length (or escape-code length) of tables 0-4 / 5-9 in
+                                        // 12-bit slots, then 1 in the slot of every table that escapes this magnitude
+    const uint8_t *band_of_line;        // [M]
     EncConsts ec;
     BandInfo bands;
 };
 
 // bitalloc.BitAlloc on a warp: lane b < NB owns band b.  Returns this lane's bits; *diff = bitDifference.
+__device__ __forceinline__ unsigned sortable32(float v) {
+    unsigned u = __float_as_uint(v);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+
+// fp32 fast mode: the SMRs are floats, so the arg-max keys are formed in float (one REDUX per maximum instead of two)
+__device__ __forceinline__ int warp_bitalloc32(double bitBudget, long long extraBits, int maxMantBits, int NB, float smrLane,
+                                               uint32_t lrms, const BandInfo &bands, long long *diff) {
+    const int lane = threadIdx.x & 31;
+    const bool inband = lane < NB;
+    int bits = 0;
+    bool valid = inband;
+    long long totalBits = (long long)(bitBudget + (double)extraBits);
+    const unsigned kMS = sortable32(-5.0f), kLR = sortable32(-15.0f);
+    while (__ballot_sync(0xffffffffu, valid) != 0u) {
+        const float v = smrLane - (float)bits * 6.f;
+        const unsigned key = inband ? sortable32(v) : 0u;
+        const unsigned mk1 = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+        const unsigned win = __ballot_sync(0xffffffffu, valid && key == mk1);
+        const int iMax = __ffs(win) - 1;
+        const unsigned k2 = inband ? sortable32(v + 6.f) : 0u;               // SMR - 6*(bits-1)
+        const unsigned mk2 = __reduce_max_sync(0xffffffffu, k2);
+        const bool below = ((lrms >> iMax) & 1u) ? (mk2 < kMS) : (mk2 < kLR);
+        const int nl = bands.lo[iMax + 1] - bands.lo[iMax];
+        const bool me = lane == iMax;
+        if (below && me) valid = false;
+        if (totalBits - nl >= 0) {
+            totalBits -= nl;
+            if (me) { bits += 1; if (bits >= maxMantBits) valid = false; }
+        } else if (me) valid = false;
+    }
+    unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);
+    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; totalBits += bands.lo[bnd + 1] - bands.lo[bnd]; }
+    if (bits == 1) bits = 0;
+    *diff = totalBits - extraBits;
+    return bits;
+}
+
 __device__ __forceinline__ int warp_bitalloc(double bitBudget, long long extraBits, int maxMantBits, int NB,
                                              int nLinesLane, double smrLane, uint32_t lrms, const BandInfo &bands,
                                              long long *diff) {
@@ -95,6 +136,16 @@ k_scan(const ScanArgs<T> a) {
     long long extraBits = a.state[s].extraBits, bitDeposit = a.state[s].bitDeposit, outOff = a.state[s].outOffset;
     const int nLinesLane = lane < NB ? a.bands.lo[lane + 1] - a.bands.lo[lane] : 0;
     const int bEnd = min(a.b0 + a.nb, nblkStream);
+    constexpr int LPL = 32;                      // lines per lane (M = 1024); M = 512 uses the first 16
+    unsigned bandsPacked[LPL / 4];
+#pragma unroll
+    for (int q = 0; q < LPL / 4; q++) {
+        unsigned v = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) { int i = (4 * q + r) * 32 + lane; v |= (unsigned)(i < M ? a.band_of_line[i] : 0) << (8 * r); }
+        bandsPacked[q] = v;
+    }
+    const int lplRun = M / 32;
 
     for (int b = a.b0; b < bEnd; b++) {
         const int64_t w = (int64_t)s * a.nb + (b - a.b0);
@@ -111,34 +162,45 @@ k_scan(const ScanArgs<T> a) {
             double smrLane = lane < NB ? (double)a.smr[wc * kMaxBands + lane] : 0.0;
             double bmaxLane = lane < NB ? (double)a.bmax[wc * kMaxBands + lane] : 0.0;
             long long diff;
-            int bits = warp_bitalloc(ec.bitBudget, extraBits, ec.maxMantBits, NB, nLinesLane, smrLane, lrms, a.bands, &diff);
+            int bits;
+            if constexpr (sizeof(T) == 4) bits = warp_bitalloc32(ec.bitBudget, extraBits, ec.maxMantBits, NB, (float)smrLane, lrms, a.bands, &diff);
+            else bits = warp_bitalloc(ec.bitBudget, extraBits, ec.maxMantBits, NB, nLinesLane, smrLane, lrms, a.bands, &diff);
             extraBits += diff;                                             // codec.py:260
             int sfl = scale_factor(bmaxLane, ec.nScaleBits, bits);       // codec.py:274
             if (lane < NB) { a.ba[wc * kMaxBands + lane] = (uint8_t)bits; a.sf[wc * kMaxBands + lane] = (uint8_t)sfl; }
-            // code lengths under the 10 tables
-            unsigned tot[kNTables];
-#pragma unroll
-            for (int t = 0; t < kNTables; t++) tot[t] = 0;
+            // code lengths under the 10 tables.  Lane l owns lines 32*j + l; per line one 32-byte LUT entry gives all ten
+            // lengths in 12-bit packed slots (a lane's 32 lines cannot overflow a slot), escapes add bitAlloc raw bits
+            // (Huffman.py:292-298).  The 16 lines of a chunk are independent, so their loads overlap.
             const T *x = a.lines + wc * M;
-            unsigned active = __ballot_sync(0xffffffffu, lane < NB && bits > 0);
-            int nMant = 0, origin = 0;
-            while (active) {
-                int bd = __ffs(active) - 1;
-                active &= active - 1;
-                int bab = __shfl_sync(0xffffffffu, bits, bd);
-                int sfb = __shfl_sync(0xffffffffu, sfl, bd);
-                int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
-                nMant += hi - lo;
-                origin += bab * (hi - lo);
-                for (int i = lo + lane; i < hi; i += 32) {
-                    unsigned mag = mant_mag(fabs((double)x[i]), sfb, largestScale, bab);
-                    unsigned long long lw = mag < (unsigned)kLenLutSize ? __ldg(a.lenLut + mag) : 0ull;
+            unsigned long long acc0 = 0, acc1 = 0;
 #pragma unroll
-                    for (int t = 0; t < kNTables; t++) {
-                        unsigned l = (unsigned)(lw >> (5 * t)) & 31u;
-                        tot[t] += l ? l : (unsigned)(ec.esc_len[t] + bab);    // Huffman.py:292-298
+            for (int j0 = 0; j0 < LPL; j0 += 16) {
+                if (j0 >= lplRun) break;
+                T xv[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) xv[j] = x[(j0 + j) * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int bd = (bandsPacked[(j0 + j) >> 2] >> (8 * ((j0 + j) & 3))) & 0xff;
+                    const int bab = __shfl_sync(0xffffffffu, bits, bd);
+                    const int sfb = __shfl_sync(0xffffffffu, sfl, bd);
+                    if (bab > 0) {
+                        unsigned mag = mant_mag(fabs((double)xv[j]), sfb, largestScale, bab);
+                        const ulonglong2 *ep = reinterpret_cast<const ulonglong2 *>(a.lenLut4 + (mag < (unsigned)kLenLutSize ? mag : (unsigned)kLenLutSize));
+                        const ulonglong2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+                        acc0 += e0.x + e1.x * (unsigned long long)bab;
+                        acc1 += e0.y + e1.y * (unsigned long long)bab;
                     }
                 }
+            }
+            unsigned tot[kNTables];
+#pragma unroll
+            for (int t = 0; t < 5; t++) { tot[t] = (unsigned)(acc0 >> (12 * t)) & 0xfffu; tot[5 + t] = (unsigned)(acc1 >> (12 * t)) & 0xfffu; }
+            int nMant = 0, origin = 0;
+            {
+                int nm = (lane < NB && bits > 0) ? nLinesLane : 0;
+                nMant = __reduce_add_sync(0xffffffffu, nm);
+                origin = __reduce_add_sync(0xffffffffu, nm * bits);
             }
             unsigned best = 0;
             int bestID = 1;
