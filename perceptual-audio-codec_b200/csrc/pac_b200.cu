@@ -57,6 +57,10 @@ struct PacCtx {
     EncConsts ec{};
     cudaStream_t stream = nullptr;
     cudaStream_t ownStream = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr;      // internal streams: analysis / scan+pack of consecutive tiles overlap
+    cudaEvent_t evStart = nullptr;
+    std::vector<cudaEvent_t> evA, evB;
+    cudaStream_t launchStream = nullptr;          // stream the launch helpers currently target (default: ctx->stream)
     std::string err;
     int64_t launches = 0;
     int numSMs = 148;
@@ -122,8 +126,9 @@ static void timing_flush(PacCtx *ctx) {      // call only after the stream has b
 }
 struct KTimer {
     PacCtx *ctx; int kind; cudaEvent_t a{}, b{};
-    KTimer(PacCtx *c, int k) : ctx(c), kind(k) { if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, ctx->stream); } }
-    ~KTimer() { if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->pending.push_back({a, b, kind}); } }
+    cudaStream_t st;
+    KTimer(PacCtx *c, int k) : ctx(c), kind(k), st(c->launchStream ? c->launchStream : c->stream) { if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, st); } }
+    ~KTimer() { if (ctx->timing) { cudaEventRecord(b, st); ctx->pending.push_back({a, b, kind}); } }
 };
 
 extern "C" int pac_set_stream(PacCtx *ctx, void *stream) {
@@ -152,6 +157,8 @@ extern "C" int pac_timing_get(PacCtx *ctx, double *ms, int64_t *count) {
     for (int i = 0; i < PAC_NKINDS; i++) { ms[i] = ctx->kms[i]; count[i] = ctx->kcount[i]; }
     return PAC_OK;
 }
+
+static inline cudaStream_t LS(PacCtx *ctx) { return ctx->launchStream ? ctx->launchStream : ctx->stream; }
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
@@ -504,6 +511,13 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
     ec.fixedBits = params->nScaleBits + params->nTableIDBits + NB * (params->nMantSizeBits + params->nScaleBits) + NB;
     CK(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
     ctx->stream = ctx->ownStream;
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, lo));      // analysis: lowest priority
+        CK(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, hi));      // scan + pack: highest
+        CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
+    }
     int rc = build_huffman(ctx, tables);
     if (rc) return rc;
     DevTables<float> tf; DevTables<double> td;
@@ -527,6 +541,11 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); timing_flush(ctx); }
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    if (ctx->sA) cudaStreamDestroy(ctx->sA);
+    if (ctx->sB) cudaStreamDestroy(ctx->sB);
+    if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+    for (cudaEvent_t e : ctx->evA) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->evB) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
@@ -599,9 +618,10 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM>, (1 << LOGM) / 4, smem));
     if (perSM < 1) perSM = 1;
     int64_t grid = (int64_t)ctx->numSMs * perSM;
+    if (ctx->launchStream) grid = a.nwork;       // overlapped tiles: short-lived CTAs let the scan/pack kernels of the previous tile in
     if (grid > a.nwork) grid = a.nwork;
     if (grid < 1) grid = 1;
-    { KTimer kt(ctx, PAC_K_ANALYSIS); k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, ctx->stream>>>(a); }
+    { KTimer kt(ctx, PAC_K_ANALYSIS); k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, LS(ctx)>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -630,7 +650,7 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         a.band_of_line = tb.band_of_line;
     }
     constexpr int WARPS = 4;
-    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, ctx->stream>>>(a); }
+    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, LS(ctx)>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -644,7 +664,7 @@ static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
     int64_t maxg = (int64_t)ctx->numSMs * 8;
     if (grid > maxg) grid = maxg;
     if (grid < 1) grid = 1;
-    { KTimer kt(ctx, PAC_K_PACK); k_pack<T><<<(unsigned)grid, kPackWarps * 32, 0, ctx->stream>>>(a); }
+    { KTimer kt(ctx, PAC_K_PACK); k_pack<T><<<(unsigned)grid, kPackWarps * 32, 0, LS(ctx)>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -702,42 +722,66 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         CK(cudaMemcpyAsync(ctx->w_hdr.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, ctx->stream));
         CK(ctx->w_ovf.ensure((size_t)Sc * 4));
         CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)Sc * 4, ctx->stream));
-        // ---- intermediates
-        CK(ctx->w_lines.ensure((size_t)nwork * 2 * M * sizeof(T)));
-        CK(ctx->w_smr.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
-        CK(ctx->w_bmax.ensure((size_t)nwork * 2 * kMaxBands * sizeof(T)));
-        CK(ctx->w_osc.ensure((size_t)nwork * 2));
-        CK(ctx->w_lrms.ensure((size_t)nwork * 4));
+        // ---- intermediates, double-buffered by tile parity so that scan+pack of tile i (stream sB, high priority) overlap the
+        //      analysis of tile i+1 (stream sA)
+        const int nTiles = (int)((maxBlocks + TB - 1) / TB);
+        const bool overlap = !trace && nTiles > 1;
+        const int NBUF = overlap ? 2 : 1;
+        const size_t szLines = (size_t)nwork * 2 * M * sizeof(T), szBand = (size_t)nwork * 2 * kMaxBands * sizeof(T);
+        CK(ctx->w_lines.ensure(szLines * NBUF));
+        CK(ctx->w_smr.ensure(szBand * NBUF));
+        CK(ctx->w_bmax.ensure(szBand * NBUF));
+        CK(ctx->w_osc.ensure((size_t)nwork * 2 * NBUF));
+        CK(ctx->w_lrms.ensure((size_t)nwork * 4 * NBUF));
         CK(ctx->w_ba.ensure((size_t)nwork * 2 * kMaxBands));
         CK(ctx->w_sf.ensure((size_t)nwork * 2 * kMaxBands));
         CK(ctx->w_tid.ensure((size_t)nwork * 2));
         CK(ctx->w_nby.ensure((size_t)nwork * 2 * 4));
         CK(ctx->w_coff.ensure((size_t)nwork * 2 * 8));
         if (trace) { CK(ctx->w_trE.ensure((size_t)nwork * 8)); CK(ctx->w_trD.ensure((size_t)nwork * 8)); }
-        for (int b0 = 0; b0 < maxBlocks; b0 += TB) {
+        if (overlap) {
+            while ((int)ctx->evA.size() < nTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evA.push_back(e); }
+            while ((int)ctx->evB.size() < nTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evB.push_back(e); }
+            CK(cudaEventRecord(ctx->evStart, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->sA, ctx->evStart, 0));
+            CK(cudaStreamWaitEvent(ctx->sB, ctx->evStart, 0));
+        }
+        int tile = 0;
+        for (int b0 = 0; b0 < maxBlocks; b0 += TB, tile++) {
             const int nb = (maxBlocks - b0 < TB) ? (int)(maxBlocks - b0) : TB;
+            const int pbuf = overlap ? (tile & 1) : 0;
             AnalysisArgs<T> aa{};
             aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.as<int64_t>(); aa.blocks = nullptr;
             aa.S = Sc; aa.b0 = b0; aa.nb = nb; aa.nwork = (int64_t)Sc * nb;
-            aa.lines = ctx->w_lines.as<T>(); aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>();
-            aa.oscale = ctx->w_osc.as<uint8_t>(); aa.lrms = ctx->w_lrms.as<uint32_t>();
+            aa.lines = reinterpret_cast<T *>(ctx->w_lines.as<char>() + szLines * pbuf);
+            aa.smr = reinterpret_cast<T *>(ctx->w_smr.as<char>() + szBand * pbuf);
+            aa.bmax = reinterpret_cast<T *>(ctx->w_bmax.as<char>() + szBand * pbuf);
+            aa.oscale = ctx->w_osc.as<uint8_t>() + (size_t)nwork * 2 * pbuf;
+            aa.lrms = ctx->w_lrms.as<uint32_t>() + (size_t)nwork * pbuf;
             aa.dbg_mdct = nullptr; aa.dbg_bthr = nullptr;
+            if (overlap) {
+                if (tile >= 2) CK(cudaStreamWaitEvent(ctx->sA, ctx->evB[tile - 2], 0));      // buffer reuse
+                ctx->launchStream = ctx->sA;
+            }
             int rc = launch_analysis<T>(ctx, aa);
-            if (rc) return rc;
+            if (overlap) { CK(cudaEventRecord(ctx->evA[tile], ctx->sA)); CK(cudaStreamWaitEvent(ctx->sB, ctx->evA[tile], 0)); ctx->launchStream = ctx->sB; }
+            if (rc) { ctx->launchStream = nullptr; return rc; }
             ScanArgs<T> sa{};
             sa.S = Sc; sa.b0 = b0; sa.nb = nb; sa.nSamples = ctx->w_ns.as<int64_t>(); sa.state = ctx->w_state.as<StreamState>();
             sa.lines = aa.lines; sa.smr = aa.smr; sa.bmax = aa.bmax; sa.lrms = aa.lrms;
             sa.ba = ctx->w_ba.as<uint8_t>(); sa.sf = ctx->w_sf.as<uint8_t>(); sa.tableID = ctx->w_tid.as<uint8_t>();
             sa.nbytes = ctx->w_nby.as<uint32_t>(); sa.chunkOff = ctx->w_coff.as<long long>();
             sa.trExtra = trace ? ctx->w_trE.as<long long>() : nullptr; sa.trDeposit = trace ? ctx->w_trD.as<long long>() : nullptr;
-            if ((rc = launch_scan<T>(ctx, sa))) return rc;
+            if ((rc = launch_scan<T>(ctx, sa))) { ctx->launchStream = nullptr; return rc; }
             PackArgs<T> pa{};
             pa.S = Sc; pa.b0 = b0; pa.nb = nb; pa.nSamples = ctx->w_ns.as<int64_t>();
             pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
             pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = d_out; pa.cap = cap; pa.perChunk = 0;
             pa.overflow = ctx->w_ovf.as<int>(); pa.o_mant = nullptr;
             pa.header = ctx->w_hdr.as<uint8_t>(); pa.headerBytes = hdrB;
-            if ((rc = launch_pack<T>(ctx, pa))) return rc;
+            rc = launch_pack<T>(ctx, pa);
+            if (overlap) { CK(cudaEventRecord(ctx->evB[tile], ctx->sB)); ctx->launchStream = nullptr; }
+            if (rc) return rc;
             if (trace) {      // single tile (TB == maxBlocks): copy the taps of this stream group
                 CK(cudaStreamSynchronize(ctx->stream));
                 const int64_t B = maxBlocksAll;
@@ -778,6 +822,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
                 }
             }
         }
+        if (overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->evB[nTiles - 1], 0));
         // ---- results of this group
         CK(cudaMemcpyAsync(st.data(), ctx->w_state.p, (size_t)Sc * sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
         std::vector<int> ovf(Sc);
