@@ -58,6 +58,9 @@ struct PacCtx {
     cudaStream_t stream = nullptr;
     cudaStream_t ownStream = nullptr;
     cudaStream_t sA = nullptr, sB = nullptr;      // internal streams: analysis / scan+pack of consecutive tiles overlap
+    cudaStream_t sC = nullptr;                    // copy stream: H2D of the next stream group / D2H of the previous one
+    cudaEvent_t evH[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
+    DBuf w_pcm2, w_out2;
     cudaEvent_t evStart = nullptr;
     std::vector<cudaEvent_t> evA, evB;
     cudaStream_t launchStream = nullptr;          // stream the launch helpers currently target (default: ctx->stream)
@@ -517,6 +520,8 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
         CK(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, lo));      // analysis: lowest priority
         CK(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, hi));      // scan + pack: highest
         CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&ctx->sC, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->evH[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evD[i], cudaEventDisableTiming)); }
     }
     int rc = build_huffman(ctx, tables);
     if (rc) return rc;
@@ -543,6 +548,9 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     if (ctx->sA) cudaStreamDestroy(ctx->sA);
     if (ctx->sB) cudaStreamDestroy(ctx->sB);
+    if (ctx->sC) cudaStreamDestroy(ctx->sC);
+    for (int i = 0; i < 2; i++) { if (ctx->evH[i]) cudaEventDestroy(ctx->evH[i]); if (ctx->evD[i]) cudaEventDestroy(ctx->evD[i]); }
+    ctx->w_pcm2.release(); ctx->w_out2.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     for (cudaEvent_t e : ctx->evA) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->evB) cudaEventDestroy(e);
@@ -687,10 +695,37 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     const int64_t workBudget = 1 << 18;                       // (stream, block) items resident at once
     int Sg = S;
     const int64_t stagingLimit = (int64_t)24 << 30;
-    if (!pcmDev) { int64_t per = stride * 4 + (outDev ? 0 : cap); int64_t lim = stagingLimit / (per > 0 ? per : 1); if (lim < 1) lim = 1; if (Sg > lim) Sg = (int)lim; }
+    const bool staged = !pcmDev || !outDev;
+    if (staged) {
+        // host buffers: groups are pipelined (H2D of group g+1 and D2H of group g-1 run on the copy stream while group g
+        // computes), so use about eight groups, each double-buffered within the staging limit
+        int64_t per = (pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap);
+        int64_t lim = stagingLimit / (2 * (per > 0 ? per : 1));
+        if (lim < 1) lim = 1;
+        int want = S >= 2048 ? S / 8 : (S >= 64 ? (S + 3) / 4 : S);
+        if (trace) want = S;
+        Sg = (int)(want < lim ? want : lim);
+        if (Sg < 1) Sg = 1;
+    }
     if (Sg > 8192) Sg = 8192;
     int status = PAC_OK;
-    for (int s0 = 0; s0 < S; s0 += Sg) {
+    const int nGroups = (S + Sg - 1) / Sg;
+    auto h2d_group = [&](int g) -> cudaError_t {            // stage group g's PCM on the copy stream
+        const int s0g = g * Sg, Scg = (S - s0g < Sg) ? S - s0g : Sg;
+        DBuf &buf = (g & 1) ? ctx->w_pcm2 : ctx->w_pcm;
+        cudaError_t e = buf.ensure((size_t)Sg * stride * 4 + 16);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(buf.p, pcm + (int64_t)s0g * stride * 2, (size_t)Scg * stride * 4, cudaMemcpyHostToDevice, ctx->sC);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ctx->evH[g & 1], ctx->sC);
+    };
+    if (staged) {
+        CK(cudaEventRecord(ctx->evStart, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->sC, ctx->evStart, 0));
+        if (!pcmDev) CK(h2d_group(0));
+    }
+    int grp = 0;
+    for (int s0 = 0; s0 < S; s0 += Sg, grp++) {
         const int Sc = (S - s0 < Sg) ? S - s0 : Sg;
         int64_t maxBlocks = 0;
         for (int s = 0; s < Sc; s++) { int64_t nb = pac_num_blocks(ctx, nSamples[s0 + s]); if (nb > maxBlocks) maxBlocks = nb; }
@@ -703,13 +738,18 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         const int16_t *d_pcm;
         if (pcmDev) d_pcm = pcm + (int64_t)s0 * stride * 2;
         else {
-            CK(ctx->w_pcm.ensure((size_t)Sc * stride * 4 + 16));
-            CK(cudaMemcpyAsync(ctx->w_pcm.p, pcm + (int64_t)s0 * stride * 2, (size_t)Sc * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
-            d_pcm = ctx->w_pcm.as<int16_t>();
+            d_pcm = ((grp & 1) ? ctx->w_pcm2 : ctx->w_pcm).as<int16_t>();
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->evH[grp & 1], 0));               // this group's PCM has landed
+            if (grp + 1 < nGroups) CK(h2d_group(grp + 1));                              // next group's copy overlaps this group's kernels
         }
         uint8_t *d_out;
         if (outDev) d_out = out + (int64_t)s0 * cap;
-        else { CK(ctx->w_out.ensure((size_t)Sc * cap)); d_out = ctx->w_out.as<uint8_t>(); }
+        else {
+            DBuf &ob = (grp & 1) ? ctx->w_out2 : ctx->w_out;
+            CK(ob.ensure((size_t)Sg * cap));
+            d_out = ob.as<uint8_t>();
+            if (grp >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->evD[grp & 1], 0));  // its previous contents have been copied out
+        }
         CK(ctx->w_ns.ensure((size_t)Sc * 8));
         CK(cudaMemcpyAsync(ctx->w_ns.p, nSamples + s0, (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<StreamState> st(Sc);
@@ -835,11 +875,13 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             if (ovf[s] || st[s].outOffset > cap) { status = PAC_E_OVERFLOW; outBytes[s0 + s] = -st[s].outOffset; }
             else if (st[s].outOffset > maxBytes) maxBytes = st[s].outOffset;
         }
-        if (!outDev && maxBytes > 0) {
-            CK(cudaMemcpy2DAsync(out + (int64_t)s0 * cap, (size_t)cap, d_out, (size_t)cap, (size_t)maxBytes, (size_t)Sc, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+        if (!outDev) {                                    // the kernels of this group are complete (stream synchronised above)
+            if (maxBytes > 0)
+                CK(cudaMemcpy2DAsync(out + (int64_t)s0 * cap, (size_t)cap, d_out, (size_t)cap, (size_t)maxBytes, (size_t)Sc, cudaMemcpyDeviceToHost, ctx->sC));
+            CK(cudaEventRecord(ctx->evD[grp & 1], ctx->sC));
         }
     }
+    if (staged) CK(cudaStreamSynchronize(ctx->sC));
     if (status == PAC_E_OVERFLOW) ctx->err = "output capacity too small for at least one stream (outBytes[s] = -needed)";
     return status;
 }
