@@ -292,7 +292,9 @@ def main():
     ach = blocks_local * algo / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
     traffic = ncu_traffic()
     roof = {"bound": "hbm", "kernel": "k_analysis (window+MDCT+M/S decision+SMR)", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "peak_source": peak_src, "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+            "frac": ach / peak, "peak_source": peak_src,
+            "traffic": (traffic["dram_bytes_per_block"] * blocks_local / max(a_cnt, 1)) if traffic and traffic.get("dram_bytes_per_block") else None,
+            "traffic_source": traffic.get("source") if traffic else None,
             "algorithmic_bytes_per_block": algo, "blocks_per_launch": blocks_local / max(a_cnt, 1),
             "avg_launch_ms": a_ms / max(a_cnt, 1), "launches": a_cnt,
             "note": "SMR is transcendental-bound, not HBM-bound (SURVEY.md App. E); kernel time split: "
