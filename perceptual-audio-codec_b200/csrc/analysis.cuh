@@ -220,6 +220,12 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float K = 0.33219280948873623f;           // log2(10)/10
     auto &fs = sm.fs;
+    // static per-thread table rows, fetched now so that their latency hides behind steps 1-2
+    const int k0 = 4 * tid;
+    const uint4 beu = ft.binEU[tid];                       // per bin: eL (as int16) | eU << 16
+    const float4 bt0 = ft.binTab[k0], bt1 = ft.binTab[k0 + 1], bt2 = ft.binTab[k0 + 2], bt3 = ft.binTab[k0 + 3];
+    const uint4 lg = ft.lineGather[tid];                  // per line: kLa | nL << 10 | kUa << 12 | nU << 22
+    const uint4 lp = ft.linePlat[tid];                    // per line: pa | pb << 16
     // 1. power spectrum (optionally of the Hann-tapped spectrum)
     {
         const float2 hw = tb.hann_w, hwc = cconj(tb.hann_w);
@@ -232,7 +238,8 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     }
     __syncthreads();
     // 2. findpeaks on this thread's 4 bins; dense A / V / Wq; ordered list of the loud maskers
-    const int k0 = 4 * tid;
+    const unsigned beuq[4] = {beu.x, beu.y, beu.z, beu.w};
+    const float4 btq[4] = {bt0, bt1, bt2, bt3};
     unsigned loudf = 0;
     float c0s[4], ups[4], Aq[4];
     {
@@ -253,8 +260,8 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
                 const float c0 = (pmv - drop - 96.0f) * K;
                 const float lev = 0.367f * fmaxf(pmv - 40.0f, 0.f);
                 Av = ex2_approx(c0);
-                const int el = ft.eL[k], eu = ft.eU[k];
-                const float4 bt = ft.binTab[k];
+                const int el = (int)(short)(beuq[q] & 0xffffu), eu = (int)(beuq[q] >> 16);
+                const float4 bt = btq[q];
                 if (el >= 0) Vv = ex2_approx(c0 + bt.x);
                 if (eu < M) {
                     if (lev > 0.f) { loudf |= 1u << q; ups[q] = (lev - 27.0f) * K; c0s[q] = c0; }
@@ -287,10 +294,8 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     for (int q = 0; q < 4; q++) {
         fs.loudPrefix[k0 + q] = (unsigned short)offs;
         if (loudf & (1u << q)) {
-            const int k = k0 + q;
-            const float4 bt = ft.binTab[k];
-            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], bt.z, bt.w);
-            fs.loudEU[offs] = ft.eU[k];
+            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], btq[q].z, btq[q].w);
+            fs.loudEU[offs] = (short)(beuq[q] >> 16);
             offs++;
         }
     }
@@ -299,8 +304,6 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     // 3. per-line gathers (deterministic order) + plateau + the two scans; thread t owns lines 4t .. 4t+3
     {
         float uD[4], uA[4], pl[4];
-        const uint4 lg = ft.lineGather[tid];              // per line: kLa | nL << 10 | kUa << 12 | nU << 22
-        const uint4 lp = ft.linePlat[tid];                // per line: pa | pb << 16
         const unsigned lgq[4] = {lg.x, lg.y, lg.z, lg.w}, lpq[4] = {lp.x, lp.y, lp.z, lp.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {

@@ -58,6 +58,7 @@ struct FastTables {
     const short *lineTab;        // [6][M] per line: kLa,nL (bins entering the down-scan here), kUa,nU (up-scan), pa,pb (plateau bins)
     const short *kcountU;        // [M+1] kcountU[i] = number of bins with eU <= i-1 ... see host builder (prefix over lines)
     const float4 *binTab;        // [M] per bin: (xL, xU, zpeak_hi, zpeak_lo)
+    const uint4 *binEU;          // [NT] per thread, per bin: (uint16)eL | eU << 16
     const float2 *lineZ;         // [M] per line: Bark position as hi + lo floats
     const uint4 *lineGather;     // [NT] per scan thread, per line: kLa | nL << 10 | kUa << 12 | nU << 22
     const uint4 *linePlat;       // [NT] per scan thread, per line: pa | pb << 16 (plateau bin window)

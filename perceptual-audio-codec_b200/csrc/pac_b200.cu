@@ -306,6 +306,8 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         linePlat[i] = (unsigned)lineTab[4 * M + i] | ((unsigned)lineTab[5 * M + i] << 16);
     }
     if (M > 1024) FAIL(PAC_E_ARG, "fast tables pack bin indices in 10 bits");
+    std::vector<unsigned> binEU(M);
+    for (int k = 0; k < M; k++) binEU[k] = ((unsigned)(unsigned short)eL[k]) | ((unsigned)(unsigned short)eU[k] << 16);
     std::vector<float> binTab(4 * M), lineZ(2 * M);
     for (int k = 0; k < M; k++) {
         float zh = (float)zp[k];
@@ -334,7 +336,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         fsd.dev.omA[c] = (c >= 1 && c < NW) ? om(128 * c - 1, 128 * c + 127) : 0.f;
     }
     size_t bytes = (size_t)M * 2 * 2 + (size_t)M * 4 * 2 + (size_t)6 * M * 2 + (size_t)(M + 1) * 2 + 64 + (sD.size() + sA.size()) * 4 + 64 +
-                   binTab.size() * 4 + lineZ.size() * 4 + (lineGather.size() + linePlat.size()) * 4 + 256;
+                   binTab.size() * 4 + lineZ.size() * 4 + (lineGather.size() + linePlat.size() + binEU.size()) * 4 + 256;
     std::vector<unsigned char> host(bytes + 256, 0);
     size_t o = 0;
     auto put = [&](const void *src, size_t n) { o = (o + 15) & ~(size_t)15; memcpy(host.data() + o, src, n); size_t r = o; o += n; return r; };
@@ -343,6 +345,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
     size_t o_sD = put(sD.data(), sD.size() * 4), o_sA = put(sA.data(), sA.size() * 4);
     size_t o_bt = put(binTab.data(), binTab.size() * 4), o_lz = put(lineZ.data(), lineZ.size() * 4);
     size_t o_lg = put(lineGather.data(), lineGather.size() * 4), o_lp = put(linePlat.data(), linePlat.size() * 4);
+    size_t o_be = put(binEU.data(), binEU.size() * 4);
     CK(cudaMalloc(&fsd.mem, o + 16));
     CK(cudaMemcpy(fsd.mem, host.data(), o, cudaMemcpyHostToDevice));
     unsigned char *d = reinterpret_cast<unsigned char *>(fsd.mem);
@@ -351,6 +354,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
     fsd.dev.lineTab = reinterpret_cast<const short *>(d + o_lt); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
     fsd.dev.sD = reinterpret_cast<const float *>(d + o_sD); fsd.dev.sA = reinterpret_cast<const float *>(d + o_sA);
     fsd.dev.binTab = reinterpret_cast<const float4 *>(d + o_bt); fsd.dev.lineZ = reinterpret_cast<const float2 *>(d + o_lz);
+    fsd.dev.binEU = reinterpret_cast<const uint4 *>(d + o_be);
     fsd.dev.lineGather = reinterpret_cast<const uint4 *>(d + o_lg); fsd.dev.linePlat = reinterpret_cast<const uint4 *>(d + o_lp);
     return PAC_OK;
 }
