@@ -463,9 +463,95 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             }
         }
         __syncthreads();
+        int osc0 = 0, osc1 = 0;
+        auto sectionC = [&]() {
+            // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
+            if constexpr (!FAST) {
+                for (int e = tid; e < 2 * N; e += NT) {
+                    int ch = e / N, n = e - ch * N;
+                    xt[ch * XS + n] *= tb.sinw[n];
+                }
+                __syncthreads();
+            }
+            T mx[2] = {0, 0};
+            if constexpr (sizeof(T) == 8) {
+                for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
+                    int ch = e / H, n = e - ch * H;
+                    const T *x = xt + ch * XS;
+                    int m0 = 2 * n, m1 = M - 1 - 2 * n;
+                    T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
+                    T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
+                    sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
+                }
+                __syncthreads();
+                fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
+                for (int e = tid; e < 2 * H; e += NT) {
+                    int ch = e / H, k = e - ch * H;
+                    T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+                    T v0 = ((T)2 / (T)N) * y.x, v1 = -((T)2 / (T)N) * y.y;
+                    sm.Lb[ch][2 * k] = v0;
+                    sm.Lb[ch][M - 1 - 2 * k] = v1;
+                    T m = fmax(fabs(v0), fabs(v1));
+                    if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
+                }
+            } else {
+                // fp32 mode: an fp32 FFT leaves an error floor of ~1e-7 x (largest line) on EVERY line, i.e. far more than
+                // 1e-5 relative on the weak high-frequency lines.  The MDCT is ~1% of the block's work, so it is done in
+                // fp64 (fold, twiddles, butterflies) and only then rounded to fp32.
+                double2 *Wd = reinterpret_cast<double2 *>(&sm.W[0][0]);       // [2][H] double2 = 16 KB <= sizeof(W)
+                const DevTables<double> &td = a.tabd;
+                // PCM input: the exact int16 code is recovered from the float sample in shared memory (|code| <= 32767 fits a
+                // float exactly) and widened, so the fold sees the same doubles as the fp64 mode without a second trip to
+                // global memory.  Per-block API (arbitrary doubles): re-read them.
+                const DevTables<double> &tdd = a.tabd;
+                auto xd = [&](int ch, int n) -> double {
+                    double v;
+                    if (a.pcm) v = (double)__float2int_rn(xt[ch * XS + n] * 32767.5f) * (2.0 / 65535.0);
+                    else v = a.blocks[w * 2 * N + ch * N + n];
+                    return v * tdd.sinw[n];
+                };
+                for (int e = tid; e < 2 * H; e += NT) {
+                    int ch = e / H, n = e - ch * H;
+                    int m0 = 2 * n, m1 = M - 1 - 2 * n;
+                    double u0 = m0 < H ? -xd(ch, 3 * H - 1 - m0) - xd(ch, 3 * H + m0) : xd(ch, m0 - H) - xd(ch, 2 * H - 1 - (m0 - H));
+                    double u1 = m1 < H ? -xd(ch, 3 * H - 1 - m1) - xd(ch, 3 * H + m1) : xd(ch, m1 - H) - xd(ch, 2 * H - 1 - (m1 - H));
+                    Wd[ch * H + n] = cmul(mk2<double>(u0, u1), td.mdct_pre[n]);
+                }
+                __syncthreads();
+                fft_dif<double, LOGM - 1, NT>(Wd, 2, H, td.tw, 2);
+                double mxd[2] = {0, 0};
+                for (int e = tid; e < 2 * H; e += NT) {
+                    int ch = e / H, k = e - ch * H;
+                    double2 y = cmul(Wd[ch * H + fft_pos<LOGM - 1>(k)], td.mdct_post[k]);
+                    double v0 = (2.0 / (double)N) * y.x, v1 = -(2.0 / (double)N) * y.y;
+                    // kept in fp32 up to the power-of-two overall scale: rounding to fp32 commutes with that scaling
+                    sm.Lb[ch][2 * k] = (T)v0;
+                    sm.Lb[ch][M - 1 - 2 * k] = (T)v1;
+                    double m = fmax(fabs(v0), fabs(v1));
+                    if (ch == 0) mxd[0] = fmax(mxd[0], m); else mxd[1] = fmax(mxd[1], m);
+                }
+                mx[0] = (T)mxd[0]; mx[1] = (T)mxd[1];
+                // the overall scale only needs max|line|; its fp32 rounding can move the quantiser boundary by 6e-8 relative
+            }
+            mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
+            if (lane == 0) { sm.red[warp] = mx[0]; sm.red[32 + warp] = mx[1]; }
+            __syncthreads();
+            if (tid < 2) {
+                T m = 0;
+                for (int i = 0; i < NW; i++) m = fmax(m, sm.red[32 * tid + i]);
+                sm.oscale[tid] = scale_factor((double)m, a.nScaleBits, 5);   // codec.py:245: ScaleFactor(maxLine, nScaleBits) with the default nMantBits=5
+            }
+            __syncthreads();
+            osc0 = sm.oscale[0]; osc1 = sm.oscale[1];
+            for (int e = tid; e < 2 * M; e += NT) {
+                int ch = e / M, i = e - ch * M;
+                sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
+            }
+        };
+        if constexpr (FAST) sectionC();       // fp32: MDCT first, while x is still in shared memory (the FFT batch below runs in place)
         // ------------------------------------------------ B. raw FFTs -> LRMS decision (codec.py:96-102)
         // fp64: raw FFTs of L, R in W.  fp32: the raw FFTs run IN PLACE in XF and, in the same batch of four, the FFTs of the
-        // sine*Hann windowed channels in W (the fp32 MDCT re-reads the samples from global memory, so x is not needed later).
+        // sine*Hann windowed channels in W (the fp32 MDCT has already consumed x).
         T2(*RAW)[M + 2] = FAST ? sm.XF : sm.W;
         for (int e = tid; e < 2 * M; e += NT) {
             int ch = e / M, m = e - ch * M;
@@ -493,8 +579,12 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             }
             dr = warp_sum(dr); di = warp_sum(di); sr = warp_sum(sr); si = warp_sum(si);
             if (lane == 0) {
-                double dd = hypot((double)dr, (double)di), ss = hypot((double)sr, (double)si);
-                if (dd < 0.8 * ss) atomicOr(&sm.lrms, 1u << bd);
+                if constexpr (FAST) {
+                    if (dr * dr + di * di < 0.64f * (sr * sr + si * si)) atomicOr(&sm.lrms, 1u << bd);
+                } else {
+                    double dd = hypot((double)dr, (double)di), ss = hypot((double)sr, (double)si);
+                    if (dd < 0.8 * ss) atomicOr(&sm.lrms, 1u << bd);
+                }
             }
         }
         __syncthreads();
@@ -505,91 +595,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             }
             __syncthreads();
         }
-        // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
-        if constexpr (!FAST) {
-            for (int e = tid; e < 2 * N; e += NT) {
-                int ch = e / N, n = e - ch * N;
-                xt[ch * XS + n] *= tb.sinw[n];
-            }
-            __syncthreads();
-        }
-        T mx[2] = {0, 0};
-        if constexpr (sizeof(T) == 8) {
-            for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
-                int ch = e / H, n = e - ch * H;
-                const T *x = xt + ch * XS;
-                int m0 = 2 * n, m1 = M - 1 - 2 * n;
-                T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
-                T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
-                sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
-            }
-            __syncthreads();
-            fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
-            for (int e = tid; e < 2 * H; e += NT) {
-                int ch = e / H, k = e - ch * H;
-                T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
-                T v0 = ((T)2 / (T)N) * y.x, v1 = -((T)2 / (T)N) * y.y;
-                sm.Lb[ch][2 * k] = v0;
-                sm.Lb[ch][M - 1 - 2 * k] = v1;
-                T m = fmax(fabs(v0), fabs(v1));
-                if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
-            }
-        } else {
-            // fp32 mode: an fp32 FFT leaves an error floor of ~1e-7 x (largest line) on EVERY line, i.e. far more than
-            // 1e-5 relative on the weak high-frequency lines.  The MDCT is ~1% of the block's work, so it is done in
-            // fp64 straight from the source samples (re-read through L1/L2) and only then rounded to fp32.
-            double2 *Wd = reinterpret_cast<double2 *>(&sm.W[0][0]);       // [2][H] double2 = 16 KB <= sizeof(W)
-            const DevTables<double> &td = a.tabd;
-            auto xd = [&](int ch, int n) -> double {
-                double v;
-                if (a.pcm) {
-                    const int64_t ns = a.nSamples[s];
-                    const int64_t si = (int64_t)(b - 1) * M + n;
-                    int pv = (si >= 0 && si < ns) ? __ldg(reinterpret_cast<const int *>(a.pcm) + (int64_t)s * a.strideSamples + si) : 0;
-                    int c = ch ? (pv >> 16) : (int)(short)(pv & 0xffff);
-                    int code = c < 0 ? -c : c;
-                    if (code & 32768) code -= 32768;
-                    v = (double)(c < 0 ? -code : code) * (2.0 / 65535.0);      // fp32 mode: 1 ulp of a double is irrelevant
-                } else v = a.blocks[w * 2 * N + ch * N + n];
-                return v * td.sinw[n];
-            };
-            for (int e = tid; e < 2 * H; e += NT) {
-                int ch = e / H, n = e - ch * H;
-                int m0 = 2 * n, m1 = M - 1 - 2 * n;
-                double u0 = m0 < H ? -xd(ch, 3 * H - 1 - m0) - xd(ch, 3 * H + m0) : xd(ch, m0 - H) - xd(ch, 2 * H - 1 - (m0 - H));
-                double u1 = m1 < H ? -xd(ch, 3 * H - 1 - m1) - xd(ch, 3 * H + m1) : xd(ch, m1 - H) - xd(ch, 2 * H - 1 - (m1 - H));
-                Wd[ch * H + n] = cmul(mk2<double>(u0, u1), td.mdct_pre[n]);
-            }
-            __syncthreads();
-            fft_dif<double, LOGM - 1, NT>(Wd, 2, H, td.tw, 2);
-            double mxd[2] = {0, 0};
-            for (int e = tid; e < 2 * H; e += NT) {
-                int ch = e / H, k = e - ch * H;
-                double2 y = cmul(Wd[ch * H + fft_pos<LOGM - 1>(k)], td.mdct_post[k]);
-                double v0 = (2.0 / (double)N) * y.x, v1 = -(2.0 / (double)N) * y.y;
-                // kept in fp32 up to the power-of-two overall scale: rounding to fp32 commutes with that scaling
-                sm.Lb[ch][2 * k] = (T)v0;
-                sm.Lb[ch][M - 1 - 2 * k] = (T)v1;
-                double m = fmax(fabs(v0), fabs(v1));
-                if (ch == 0) mxd[0] = fmax(mxd[0], m); else mxd[1] = fmax(mxd[1], m);
-            }
-            mx[0] = (T)mxd[0]; mx[1] = (T)mxd[1];
-            // the overall scale only needs max|line|; its fp32 rounding can move the quantiser boundary by 6e-8 relative
-        }
-        mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
-        if (lane == 0) { sm.red[warp] = mx[0]; sm.red[32 + warp] = mx[1]; }
-        __syncthreads();
-        if (tid < 2) {
-            T m = 0;
-            for (int i = 0; i < NW; i++) m = fmax(m, sm.red[32 * tid + i]);
-            sm.oscale[tid] = scale_factor((double)m, a.nScaleBits, 5);   // codec.py:245: ScaleFactor(maxLine, nScaleBits) with the default nMantBits=5
-        }
-        __syncthreads();
-        const int osc0 = sm.oscale[0], osc1 = sm.oscale[1];
-        for (int e = tid; e < 2 * M; e += NT) {
-            int ch = e / M, i = e - ch * M;
-            sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
-        }
+        if constexpr (!FAST) sectionC();
         if constexpr (!FAST) {
             // ------------------------------------------------ D. Hann on the sine-windowed data (psychoac.py:428) + FFT
             for (int e = tid; e < 2 * M; e += NT) {
