@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--decode", action="store_true", help="also time decode-only throughput of the coded corpus (extra 'decode' key)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -259,6 +260,32 @@ def main():
     value = audio_s * args.steps / elapsed
     total_bytes = int(counts.sum().item())
 
+    # ---- decode-only throughput (BASELINE.json configs[4]): the coded images are decoded where pac_encode_batch left them
+    dec = None
+    if args.decode:
+        ob_h = counts[mine].cpu().numpy()
+        beg = np.arange(len(mine), dtype=np.int64) * cap
+        pcm_out = torch.empty(len(mine), nblk * 1024 + 1024, 2, dtype=torch.int16, device=dev)
+        dstride = pcm_out.shape[1]
+        for _ in range(2):
+            ns, _, _ = eng.decode_batch_strided(out, beg, ob_h, pcm_out, dstride)
+        barrier()
+        eng.timing(True)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            ns, _, _ = eng.decode_batch_strided(out, beg, ob_h, pcm_out, dstride)
+        d1.record()
+        barrier()
+        tmd = eng.timing_get()
+        eng.timing(False)
+        dl = torch.tensor([d0.elapsed_time(d1) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dl, op=dist.ReduceOp.MAX)
+        dec = {"value": audio_s * args.steps / float(dl.item()), "unit": "audio-s/s", "ms_per_step": float(dl.item()) / args.steps * 1e3,
+               "samples_per_stream": int(ns[0]), "kernels_ms": {k: v[0] for k, v in tmd.items() if v[1]}}
+        del pcm_out
+
     # ---- e2e through the C ABI with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -320,6 +347,8 @@ def main():
                            "cache": "inputs (%.1f GB per rank) far larger than the 126 MB L2; no flush needed" % (len(mine) * n * 4 / 1e9),
                            "coded_bytes": total_bytes},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        if dec:
+            line["decode"] = dec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -129,6 +129,10 @@ int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, con
  * hdrNumSamples/hdrSampleRate (host, may be NULL) = header fields (the WAV header uses them, pcmfile.py:103-116). */
 int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,
                      int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate);
+/* same, for images that are not back to back: stream s = pac[pacBeg[s] .. pacBeg[s]+pacLen[s]) -- e.g. the [S][cap] output
+ * of pac_encode_batch decoded in place on the device (pacBeg[s] = s*cap, pacLen[s] = outBytes[s]). */
+int pac_decode_batch_strided(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg, const int64_t *pacLen, int S, int16_t *pcm,
+                             int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate);
 /* upper bound of samples/channel a .pac image of nbytes can decode to */
 int64_t pac_decode_bound(PacCtx *ctx, int64_t nbytes);
 

@@ -84,6 +84,7 @@ def lib():
     L.pac_decode_bound.restype = C.c_int64
     L.pac_encode_batch.argtypes = [vp, vp, C.c_int64, i64p, C.c_int, vp, C.c_int64, i64p, i64p, C.POINTER(PacTrace)]
     L.pac_decode_batch.argtypes = [vp, vp, i64p, C.c_int, vp, C.c_int64, i64p, i64p, i32p]
+    L.pac_decode_batch_strided.argtypes = [vp, vp, i64p, i64p, C.c_int, vp, C.c_int64, i64p, i64p, i32p]
     L.pac_encode_blocks.argtypes = [vp, dp, C.c_int, C.POINTER(PacStreamState), i32p, i32p, i32p, i32p, i32p, i32p, u8p, C.c_int64, i32p]
     L.pac_decode_blocks.argtypes = [vp, i32p, i32p, i32p, i32p, i32p, C.c_int, dp]
     L.pac_unpack_blocks.argtypes = [vp, u8p, C.c_int64, i32p, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p]
@@ -294,6 +295,15 @@ class Engine(object):
         self._ck(lib().pac_decode_batch(self.ctx, _vp(blob), _p(off, C.c_int64), S, _vp(pcm), int(stride),
                                         _p(ns, C.c_int64), _p(hn, C.c_int64), _p(hr, C.c_int32)))
         return [(pcm[s, :ns[s]].copy(), int(hr[s]), int(hn[s])) for s in range(S)]
+
+    def decode_batch_strided(self, pac, beg, length, pcm, stride):
+        """pac / pcm: numpy arrays or CUDA tensors; stream s = pac[beg[s] : beg[s]+length[s]].  Returns (nSamples, hdrNumSamples, hdrRate)."""
+        beg = np.ascontiguousarray(beg, np.int64); length = np.ascontiguousarray(length, np.int64)
+        S = len(beg)
+        ns = np.zeros(S, np.int64); hn = np.zeros(S, np.int64); hr = np.zeros(S, np.int32)
+        self._ck(lib().pac_decode_batch_strided(self.ctx, _vp(pac), _p(beg, C.c_int64), _p(length, C.c_int64), S, _vp(pcm), int(stride),
+                                                _p(ns, C.c_int64), _p(hn, C.c_int64), _p(hr, C.c_int32)))
+        return ns, hn, hr
 
     # ---------------------------------------------------------------- per-block API
     def encode_blocks(self, data, states):

@@ -23,7 +23,8 @@ struct DecodeTables {
 // ---------------------------------------------------------------- K6a: walk the length-prefixed chunk chain
 struct IndexArgs {
     const uint8_t *pac;
-    const int64_t *pacOff;      // [S+1]
+    const int64_t *pacBeg;      // [S] first byte of each stream's file image
+    const int64_t *pacLen;      // [S] its length
     int S, hdrBytes, maxBlocks;
     int64_t *chunkPos;          // [S][maxBlocks][2] absolute byte offset of each payload
     int32_t *chunkLen;          // [S][maxBlocks][2]
@@ -38,7 +39,7 @@ __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
 __global__ void k_index(const IndexArgs a) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
-    const int64_t beg = a.pacOff[s], end = a.pacOff[s + 1];
+    const int64_t beg = a.pacBeg[s], end = beg + a.pacLen[s];
     int64_t pos = beg + a.hdrBytes;
     int nb = 0, st = 0;
     while (nb < a.maxBlocks) {
@@ -57,6 +58,14 @@ __global__ void k_index(const IndexArgs a) {
     }
     a.nBlocks[s] = nb;
     a.status[s] = st;
+}
+
+// gather every stream's file header into one contiguous buffer (one D2H instead of S)
+__global__ void k_gather_headers(const uint8_t *pac, const int64_t *pacBeg, int S, int hdrBytes, uint8_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)S * hdrBytes) return;
+    int s = (int)(i / hdrBytes), j = (int)(i - (int64_t)s * hdrBytes);
+    out[i] = pac[pacBeg[s] + j];
 }
 
 // ---------------------------------------------------------------- K6b: one thread parses one channel chunk

@@ -623,6 +623,7 @@ static void build_header(PacCtx *ctx, int64_t nSamples, uint8_t *h) {
 template <typename T, int LOGM>
 static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     size_t smem = sizeof(AnalysisSmem<T, LOGM, sizeof(T) == 4>);
+    if (const char *ex = getenv("PAC_EXTRA_SMEM")) smem += (size_t)atoi(ex);      // occupancy experiments
     static bool configured[2] = {false, false};
     (void)configured;
     CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -927,120 +928,145 @@ static int launch_synth(PacCtx *ctx, SynthArgs<T> &a, int64_t grid) {
 }
 
 template <typename T>
-static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm, int64_t stride,
+static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg, const int64_t *pacLen, int S, int16_t *pcm, int64_t stride,
                           int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
     const int M = ctx->M, hdrB = header_bytes(ctx);
     const bool pacDev = is_device_ptr(pac), pcmDev = is_device_ptr(pcm);
-    const int64_t total = pacOff[S] - pacOff[0];
-    const uint8_t *d_pac;
-    if (pacDev) d_pac = pac;
-    else {
-        CK(ctx->w_misc.ensure((size_t)total + 16));
-        CK(cudaMemcpyAsync(ctx->w_misc.p, pac + pacOff[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-        d_pac = ctx->w_misc.as<uint8_t>() - pacOff[0];
-    }
-    // headers (pacfile.py:123-151): must describe this context's layout
-    std::vector<uint8_t> hdr((size_t)S * hdrB);
-    int64_t maxLen = 0;
+    const int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
+    int64_t maxLenAll = 0;
     for (int s = 0; s < S; s++) {
-        int64_t len = pacOff[s + 1] - pacOff[s];
-        if (len < hdrB) FAIL(PAC_E_FORMAT, "stream %d shorter than a PAC header", s);
-        if (len > maxLen) maxLen = len;
-        if (pacDev) CK(cudaMemcpyAsync(hdr.data() + (size_t)s * hdrB, pac + pacOff[s], hdrB, cudaMemcpyDeviceToHost, ctx->stream));
-        else memcpy(hdr.data() + (size_t)s * hdrB, pac + pacOff[s], hdrB);
+        if (pacLen[s] < hdrB) FAIL(PAC_E_FORMAT, "stream %d shorter than a PAC header", s);
+        if (pacLen[s] > maxLenAll) maxLenAll = pacLen[s];
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    // stream groups keep the dequantised-lines intermediate bounded (~8 GB)
+    const int64_t perStream = ((maxLenAll - hdrB) / minBlock + 1) * 2 * M * (int64_t)sizeof(T);
+    int Sg = (int)(((int64_t)8 << 30) / (perStream > 0 ? perStream : 1));
+    if (Sg < 1) Sg = 1;
+    if (Sg > S) Sg = S;
     auto rd32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
     auto rd16 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); };
-    for (int s = 0; s < S; s++) {
-        const uint8_t *h = hdr.data() + (size_t)s * hdrB;
-        if (memcmp(h, "PAC ", 4)) FAIL(PAC_E_FORMAT, "stream %d: Tried to read a non-PAC file into a PACFile object", s);   // pacfile.py:130
-        if ((int)rd16(h + 8) != 2 || (int)rd32(h + 14) != M || (int)rd16(h + 18) != ctx->p.nScaleBits ||
-            (int)rd16(h + 20) != ctx->p.nMantSizeBits || (int)rd32(h + 22) != ctx->bands.nBands)
-            FAIL(PAC_E_FORMAT, "stream %d: header does not match this context's coding parameters", s);
-        for (int b = 0; b < ctx->bands.nBands; b++)
-            if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s);
-        if (hdrSampleRate) hdrSampleRate[s] = (int32_t)rd32(h + 4);
-        if (hdrNumSamples) hdrNumSamples[s] = rd32(h + 10);
-    }
-    const int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
-    const int maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
-    if ((int64_t)(maxBlocks) * M > stride && stride < pac_decode_bound(ctx, maxLen)) {
-        // the caller may legitimately pass a tighter stride when it knows the block count; checked after indexing
-    }
-    // ---- index
-    CK(ctx->w_ns.ensure((size_t)(S + 1) * 8));
-    CK(cudaMemcpyAsync(ctx->w_ns.p, pacOff, (size_t)(S + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int64_t nblkAll = (int64_t)S * maxBlocks;
-    CK(ctx->w_coff.ensure((size_t)nblkAll * 2 * 8));
-    CK(ctx->w_nby.ensure((size_t)nblkAll * 2 * 4));
-    CK(ctx->w_misc2.ensure((size_t)S * 4));   // nBlocks
-    CK(ctx->w_misc3.ensure((size_t)S * 4));   // status
-    IndexArgs ia{};
-    ia.pac = d_pac; ia.pacOff = ctx->w_ns.as<int64_t>(); ia.S = S; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
-    ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
-    ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
-    { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ia); }
-    ctx->launches++;
-    CK(cudaGetLastError());
-    std::vector<int32_t> nblk(S), stt(S);
-    CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int s = 0; s < S; s++) {
-        if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s);   // pacfile.py:184
-        if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s, (long long)nblk[s] * M);
-    }
-    // ---- unpack + dequantise
-    CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(T)));
-    CK(ctx->w_lrms.ensure((size_t)nblkAll * 4));
-    CK(cudaMemsetAsync(ctx->w_misc3.p, 0, (size_t)S * 4, ctx->stream));
-    UnpackArgs<T> ua{};
-    ua.pac = d_pac; ua.chunkPos = ia.chunkPos; ua.chunkLen = ia.chunkLen; ua.nBlocks = ia.nBlocks;
-    ua.S = S; ua.maxBlocks = maxBlocks; ua.M = M;
-    ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;   // pacfile.py:189
-    ua.lines = ctx->w_lines.as<T>(); ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
-    ua.dt = ctx->dt; ua.bands = ctx->bands;
-    {
-        int64_t nchunk = nblkAll * 2;
-        int64_t grid = (nchunk + 63) / 64;
-        if (grid > (int64_t)ctx->numSMs * 32) grid = (int64_t)ctx->numSMs * 32;
-        { KTimer kt(ctx, PAC_K_UNPACK); k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua); }
+    for (int s0 = 0; s0 < S; s0 += Sg) {
+        const int Sc = (S - s0 < Sg) ? S - s0 : Sg;
+        // ---- input: device images are used in place; host images are packed into a staging buffer
+        const uint8_t *d_pac;
+        std::vector<int64_t> beg(Sc), len(Sc);
+        int64_t maxLen = 0;
+        if (pacDev) {
+            d_pac = pac;
+            for (int s = 0; s < Sc; s++) { beg[s] = pacBeg[s0 + s]; len[s] = pacLen[s0 + s]; }
+        } else {
+            int64_t tot = 0;
+            for (int s = 0; s < Sc; s++) { beg[s] = tot; len[s] = pacLen[s0 + s]; tot += (len[s] + 15) & ~(int64_t)15; }
+            CK(ctx->w_misc.ensure((size_t)tot + 16));
+            for (int s = 0; s < Sc; s++)
+                CK(cudaMemcpyAsync(ctx->w_misc.as<uint8_t>() + beg[s], pac + pacBeg[s0 + s], (size_t)len[s], cudaMemcpyHostToDevice, ctx->stream));
+            d_pac = ctx->w_misc.as<uint8_t>();
+        }
+        for (int s = 0; s < Sc; s++) if (len[s] > maxLen) maxLen = len[s];
+        CK(ctx->w_ns.ensure((size_t)Sc * 16));
+        int64_t *d_beg = ctx->w_ns.as<int64_t>(), *d_len = d_beg + Sc;
+        CK(cudaMemcpyAsync(d_beg, beg.data(), (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_len, len.data(), (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // ---- headers (pacfile.py:123-151): must describe this context's layout
+        std::vector<uint8_t> hdr((size_t)Sc * hdrB);
+        CK(ctx->w_hdr.ensure(hdr.size()));
+        k_gather_headers<<<(unsigned)((hdr.size() + 255) / 256), 256, 0, ctx->stream>>>(d_pac, d_beg, Sc, hdrB, ctx->w_hdr.as<uint8_t>());
         ctx->launches++;
         CK(cudaGetLastError());
-    }
-    // ---- synthesis
-    int16_t *d_pcm;
-    if (pcmDev) d_pcm = pcm;
-    else { CK(ctx->w_pcm.ensure((size_t)S * stride * 4)); d_pcm = ctx->w_pcm.as<int16_t>(); }
-    CK(ctx->w_misc4.ensure((size_t)S * 8));
-    SynthArgs<T> sa{};
-    sa.lines = ua.lines; sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = S; sa.maxBlocks = maxBlocks; sa.run = 16;
-    sa.pcm = d_pcm; sa.strideSamples = stride; sa.nSamplesOut = ctx->w_misc4.as<int64_t>(); sa.rawOut = nullptr;
-    int runsPerStream = (maxBlocks + sa.run) / sa.run;
-    int rc = launch_synth<T>(ctx, sa, (int64_t)S * runsPerStream);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(stt.data(), ctx->w_misc3.p, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int s = 0; s < S; s++) {
-        if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: malformed chunk (bad table ID or code)", s);
-        nSamplesOut[s] = (int64_t)nblk[s] * M;
-    }
-    if (!pcmDev) {
+        CK(cudaMemcpyAsync(hdr.data(), ctx->w_hdr.p, hdr.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int s = 0; s < Sc; s++) {
+            const uint8_t *h = hdr.data() + (size_t)s * hdrB;
+            if (memcmp(h, "PAC ", 4)) FAIL(PAC_E_FORMAT, "stream %d: Tried to read a non-PAC file into a PACFile object", s0 + s);   // pacfile.py:130
+            if ((int)rd16(h + 8) != 2 || (int)rd32(h + 14) != M || (int)rd16(h + 18) != ctx->p.nScaleBits ||
+                (int)rd16(h + 20) != ctx->p.nMantSizeBits || (int)rd32(h + 22) != ctx->bands.nBands)
+                FAIL(PAC_E_FORMAT, "stream %d: header does not match this context's coding parameters", s0 + s);
+            for (int b = 0; b < ctx->bands.nBands; b++)
+                if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s0 + s);
+            if (hdrSampleRate) hdrSampleRate[s0 + s] = (int32_t)rd32(h + 4);
+            if (hdrNumSamples) hdrNumSamples[s0 + s] = rd32(h + 10);
+        }
+        const int maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
+        // ---- index
+        const int64_t nblkAll = (int64_t)Sc * maxBlocks;
+        CK(ctx->w_coff.ensure((size_t)nblkAll * 2 * 8));
+        CK(ctx->w_nby.ensure((size_t)nblkAll * 2 * 4));
+        CK(ctx->w_misc2.ensure((size_t)Sc * 4));   // nBlocks
+        CK(ctx->w_misc3.ensure((size_t)Sc * 4));   // status
+        IndexArgs ia{};
+        ia.pac = d_pac; ia.pacBeg = d_beg; ia.pacLen = d_len; ia.S = Sc; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
+        ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
+        ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
+        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(Sc + 127) / 128, 128, 0, ctx->stream>>>(ia); }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        std::vector<int32_t> nblk(Sc), stt(Sc);
+        CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int s = 0; s < Sc; s++) {
+            if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s0 + s);   // pacfile.py:184
+            if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s0 + s, (long long)nblk[s] * M);
+        }
+        // ---- unpack + dequantise
+        CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(T)));
+        CK(ctx->w_lrms.ensure((size_t)nblkAll * 4));
+        CK(cudaMemsetAsync(ctx->w_misc3.p, 0, (size_t)Sc * 4, ctx->stream));
+        UnpackArgs<T> ua{};
+        ua.pac = d_pac; ua.chunkPos = ia.chunkPos; ua.chunkLen = ia.chunkLen; ua.nBlocks = ia.nBlocks;
+        ua.S = Sc; ua.maxBlocks = maxBlocks; ua.M = M;
+        ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;   // pacfile.py:189
+        ua.lines = ctx->w_lines.as<T>(); ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
+        ua.dt = ctx->dt; ua.bands = ctx->bands;
+        {
+            int64_t nchunk = nblkAll * 2;
+            int64_t grid = (nchunk + 63) / 64;
+            if (grid > (int64_t)ctx->numSMs * 32) grid = (int64_t)ctx->numSMs * 32;
+            { KTimer kt(ctx, PAC_K_UNPACK); k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua); }
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        // ---- synthesis
+        int16_t *d_pcm;
+        if (pcmDev) d_pcm = pcm + (int64_t)s0 * stride * 2;
+        else { CK(ctx->w_pcm.ensure((size_t)Sc * stride * 4)); d_pcm = ctx->w_pcm.as<int16_t>(); }
+        CK(ctx->w_misc4.ensure((size_t)Sc * 8));
+        SynthArgs<T> sa{};
+        sa.lines = ua.lines; sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = Sc; sa.maxBlocks = maxBlocks; sa.run = 16;
+        sa.pcm = d_pcm; sa.strideSamples = stride; sa.nSamplesOut = ctx->w_misc4.as<int64_t>(); sa.rawOut = nullptr;
+        int runsPerStream = (maxBlocks + sa.run) / sa.run;
+        int rc = launch_synth<T>(ctx, sa, (int64_t)Sc * runsPerStream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(stt.data(), ctx->w_misc3.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         int64_t maxS = 0;
-        for (int s = 0; s < S; s++) if (nSamplesOut[s] > maxS) maxS = nSamplesOut[s];
-        if (maxS > 0) CK(cudaMemcpy2D(pcm, (size_t)stride * 4, d_pcm, (size_t)stride * 4, (size_t)maxS * 4, (size_t)S, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < Sc; s++) {
+            if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: malformed chunk (bad table ID or code)", s0 + s);
+            nSamplesOut[s0 + s] = (int64_t)nblk[s] * M;
+            if (nSamplesOut[s0 + s] > maxS) maxS = nSamplesOut[s0 + s];
+        }
+        if (!pcmDev && maxS > 0)
+            CK(cudaMemcpy2D(pcm + (int64_t)s0 * stride * 2, (size_t)stride * 4, d_pcm, (size_t)stride * 4, (size_t)maxS * 4, (size_t)Sc, cudaMemcpyDeviceToHost));
     }
     return PAC_OK;
+}
+
+extern "C" int pac_decode_batch_strided(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg, const int64_t *pacLen, int S, int16_t *pcm,
+                                        int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
+    if (!ctx) return PAC_E_ARG;
+    if (!pac || !pacBeg || !pacLen || !pcm || !nSamplesOut || S <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_batch");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return decode_batch_t<double>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+    return decode_batch_t<float>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
 }
 
 extern "C" int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,
                                 int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
     if (!ctx) return PAC_E_ARG;
-    if (!pac || !pacOff || !pcm || !nSamplesOut || S <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_batch");
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->precision == PAC_PRECISION_FP64) return decode_batch_t<double>(ctx, pac, pacOff, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
-    return decode_batch_t<float>(ctx, pac, pacOff, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+    if (!pacOff || S <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_batch");
+    std::vector<int64_t> len(S);
+    for (int s = 0; s < S; s++) len[s] = pacOff[s + 1] - pacOff[s];
+    return pac_decode_batch_strided(ctx, pac, pacOff, len.data(), S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
 }
 
 // ------------------------------------------------------------------ per-block API

@@ -344,6 +344,33 @@ def test_properties_at_scale(e64, e32, oracle):
     assert max(int(np.max(np.abs(a[0].astype(int) - b[0].astype(int)))) for a, b in zip(d32, dec)) <= 1
 
 
+def test_device_resident_encode_then_strided_decode(e64, oracle):
+    """pac_encode_batch into a device [S][cap] buffer, pac_decode_batch_strided straight from it (no host copy of the
+    images): bytes equal the oracle's, PCM equals the oracle's decode.  Ragged lengths exercise the strided index."""
+    import torch
+    lens = [44100, 1, 1024, 30000, 2048 * 7 + 5]
+    n = max(lens)
+    S = len(lens)
+    pcm = np.zeros((S, n, 2), np.int16)
+    for s, m in enumerate(lens):
+        pcm[s, :m] = synth_pcm(300 + s, m)
+    d_pcm = torch.as_tensor(pcm, device="cuda")
+    cap = e64.encode_bound(n)
+    d_out = torch.empty(S, cap, dtype=torch.uint8, device="cuda")
+    _, ob = e64.encode_batch(d_pcm, out=d_out, cap=cap, nSamples=np.array(lens, np.int64))
+    imgs = [bytes(d_out[s, :ob[s]].cpu().numpy()) for s in range(S)]
+    for s, m in enumerate(lens):
+        assert imgs[s] == oracle.encode_stream(pcm[s, :m])[0], s
+    stride = (n + 1023) // 1024 * 1024 + 1024
+    d_dec = torch.zeros(S, stride, 2, dtype=torch.int16, device="cuda")
+    ns, hn, hr = e64.decode_batch_strided(d_out, np.arange(S, dtype=np.int64) * cap, np.asarray(ob, np.int64), d_dec, stride)
+    dec = d_dec.cpu().numpy()
+    for s, m in enumerate(lens):
+        ref = oracle.decode_stream(imgs[s])[0]
+        assert ns[s] == ref.shape[0] and hn[s] == m and hr[s] == 44100
+        np.testing.assert_array_equal(dec[s, :ns[s]], ref)
+
+
 def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
     """fp32 fast mode cannot be byte exact; it must report its quantiser-code mismatch rate (north_star)."""
     import pacb200_batch as pbat
