@@ -36,28 +36,54 @@ __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
-__global__ void k_index(const IndexArgs a) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per stream.  The chain is serial (each length prefix tells where the next one is), so the warp stages a
+// 4 KB window of the image in shared memory with coalesced 16 B loads and every lane walks it redundantly from
+// there (uniform control flow); a new window is fetched only when the walk leaves the current one (~13 links).
+constexpr int kIdxWin = 4096, kIdxWarps = 4;
+
+__global__ void __launch_bounds__(32 * kIdxWarps) k_index(const IndexArgs a) {
+    __shared__ __align__(16) uint8_t win[kIdxWarps][kIdxWin];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kIdxWarps + warp;
     if (s >= a.S) return;
     const int64_t beg = a.pacBeg[s], end = beg + a.pacLen[s];
+    const uintptr_t base = (uintptr_t)a.pac;
+    const uintptr_t aEnd = (base + (uintptr_t)end + 15) & ~(uintptr_t)15;   // loads stay inside the image's 16 B granules
+    uintptr_t wlo = 0, whi = 0;                                             // window = addresses [wlo, whi)
+    uint8_t *w = win[warp];
+    auto rd = [&](int64_t p) -> uint32_t {                                  // little-endian u32 at image offset p (p+4 <= end)
+        const uintptr_t A = base + (uintptr_t)p;
+        if (A < wlo || A + 4 > whi) {
+            __syncwarp();
+            wlo = A & ~(uintptr_t)15; whi = wlo + kIdxWin;
+#pragma unroll
+            for (int k = 0; k < kIdxWin / 512; k++) {
+                uintptr_t q = wlo + (uintptr_t)(k * 512 + lane * 16);
+                if (q < aEnd) *reinterpret_cast<uint4 *>(w + k * 512 + lane * 16) = __ldg(reinterpret_cast<const uint4 *>(q));
+            }
+            __syncwarp();
+        }
+        return ld_le32(w + (A - wlo));
+    };
     int64_t pos = beg + a.hdrBytes;
     int nb = 0, st = 0;
     while (nb < a.maxBlocks) {
         int64_t p0, p1;
         uint32_t n0, n1;
         if (pos + 4 > end) break;                         // EOF on the first channel (pacfile.py:170-178)
-        n0 = ld_le32(a.pac + pos); p0 = pos + 4; pos = p0 + n0;
+        n0 = rd(pos); p0 = pos + 4; pos = p0 + n0;
         if (pos > end) { st = PAC_E_FORMAT; break; }       // pacfile.py:184
         if (pos + 4 > end) break;                         // EOF on the second channel: block is dropped
-        n1 = ld_le32(a.pac + pos); p1 = pos + 4; pos = p1 + n1;
+        n1 = rd(pos); p1 = pos + 4; pos = p1 + n1;
         if (pos > end) { st = PAC_E_FORMAT; break; }
-        int64_t o = ((int64_t)s * a.maxBlocks + nb) * 2;
-        a.chunkPos[o] = p0; a.chunkPos[o + 1] = p1;
-        a.chunkLen[o] = (int32_t)n0; a.chunkLen[o + 1] = (int32_t)n1;
+        if (lane == 0) {
+            int64_t o = ((int64_t)s * a.maxBlocks + nb) * 2;
+            *reinterpret_cast<longlong2 *>(a.chunkPos + o) = make_longlong2(p0, p1);
+            *reinterpret_cast<int2 *>(a.chunkLen + o) = make_int2((int)n0, (int)n1);
+        }
         nb++;
     }
-    a.nBlocks[s] = nb;
-    a.status[s] = st;
+    if (lane == 0) { a.nBlocks[s] = nb; a.status[s] = st; }
 }
 
 // gather every stream's file header into one contiguous buffer (one D2H instead of S)
@@ -69,22 +95,44 @@ __global__ void k_gather_headers(const uint8_t *pac, const int64_t *pacBeg, int 
 }
 
 // ---------------------------------------------------------------- K6b: one thread parses one channel chunk
+// MSB-first bit reader (bitpack.py:104-170) over global memory: a 64-bit window, topped up with aligned, clamped
+// 32-bit loads.  Reading past the chunk returns repeated bytes; `used > nbits` flags it afterwards.
 struct BitReader {
-    const uint8_t *p;
-    int64_t nbits, pos;
-    __device__ __forceinline__ uint32_t peek(int n) {      // next n (<= 24) bits, zero padded past the end
-        int64_t byte = pos >> 3;
-        int sh = (int)(pos & 7);
-        uint64_t v = 0;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            int64_t bi = byte + i;
-            uint64_t bv = (bi * 8 < nbits) ? p[bi] : 0;
-            v = (v << 8) | bv;
-        }
-        return (uint32_t)((v >> (40 - sh - n)) & ((1u << n) - 1u));
+    const uint32_t *wp, *wlast;
+    uint64_t buf;
+    int cnt;                     // valid bits at the top of buf
+    int64_t used, nbits;
+    __device__ __forceinline__ uint32_t word() {
+        uint32_t v = __ldg(wp < wlast ? wp : wlast);
+        wp++;
+        return __byte_perm(v, 0, 0x0123);
     }
-    __device__ __forceinline__ uint32_t get(int n) { uint32_t v = n ? peek(n) : 0; pos += n; return v; }
+    __device__ __forceinline__ void seek(const uint8_t *p, int64_t bitpos) {
+        uintptr_t A = (uintptr_t)p + (uintptr_t)(bitpos >> 3);
+        wp = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);
+        int off = (int)(A & 3) * 8 + (int)(bitpos & 7);
+        uint64_t hi = word(), lo = word();
+        buf = ((hi << 32) | lo) << off;
+        cnt = 64 - off;
+        used = bitpos;
+    }
+    __device__ __forceinline__ void init(const uint8_t *p, int64_t nbytes) {
+        nbits = nbytes * 8;
+        wlast = reinterpret_cast<const uint32_t *>(((uintptr_t)p + (uintptr_t)(nbytes > 0 ? nbytes - 1 : 0)) & ~(uintptr_t)3);
+        seek(p, 0);
+    }
+    __device__ __forceinline__ void fill() {              // afterwards cnt >= 33
+        if (cnt <= 32) { buf |= (uint64_t)word() << (32 - cnt); cnt += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) { return (uint32_t)(buf >> (64 - n)); }     // 1 <= n <= 32, after fill()
+    __device__ __forceinline__ void skip(int n) { buf <<= n; cnt -= n; used += n; }
+    __device__ __forceinline__ uint32_t get(int n) {      // 0 <= n <= 32
+        if (!n) return 0;
+        fill();
+        uint32_t v = peek(n);
+        skip(n);
+        return v;
+    }
 };
 
 template <typename T>
@@ -96,7 +144,9 @@ struct UnpackArgs {
     int S, maxBlocks, M;
     int nScaleBits, nMantSizeBits, nTableIDBits;
     // outputs, chunk-indexed c = (s*maxBlocks + b)*2 + ch
-    T *lines;                    // [nchunk][M] dequantised, / 2^overallScale (may be NULL)
+    uint16_t *codes;             // [nchunk][M] mantissa codes, sign at bit ba-1 (lines of zero-bit bands are NOT written)
+    uint16_t *meta;              // [nchunk][kMaxBands] sf | ba << 8
+    uint8_t *oscale;             // [nchunk]
     uint32_t *lrms;              // [nblocks] (from the LAST channel parsed, pacfile.py:216-217)
     int32_t *err;                // [S]
     int32_t *o_sf, *o_ba, *o_mant, *o_oscale, *o_tableID;   // optional raw fields (per-block API)
@@ -105,64 +155,65 @@ struct UnpackArgs {
 };
 
 template <typename T>
-__global__ void k_unpack(const UnpackArgs<T> a) {
+__global__ void __launch_bounds__(64) k_unpack(const UnpackArgs<T> a) {
     const int64_t nchunk = (int64_t)a.S * a.maxBlocks * 2;
     const int NB = a.bands.nBands, M = a.M;
-    const int largestScale = (1 << a.nScaleBits) - 1;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (int64_t)gridDim.x * blockDim.x) {
         const int64_t w = c >> 1;
         const int s = (int)(w / a.maxBlocks);
         const int b = (int)(w - (int64_t)s * a.maxBlocks);
         if (a.nBlocks && b >= a.nBlocks[s]) continue;
+        const uint8_t *p = a.pac + a.chunkPos[c];
         BitReader r;
-        r.p = a.pac + a.chunkPos[c];
-        r.nbits = (int64_t)a.chunkLen[c] * 8;
-        r.pos = 0;
+        r.init(p, a.chunkLen[c]);
+        bool bad = a.chunkLen[c] <= 0;
         const int oscale = (int)r.get(a.nScaleBits);                  // pacfile.py:187
         const int tid = (int)r.get(a.nTableIDBits);                   // :190
-        bool bad = tid < 1 || tid > kNTables;
+        bad |= tid < 1 || tid > kNTables;
         const uint32_t *lut = a.dt.lut + (size_t)(bad ? 0 : tid - 1) * (1 << kLutBits);
-        const double rescale = 1.0 / (double)(1 << oscale);           // codec.py:32,43 (exact power of two)
-        T *out = a.lines ? a.lines + c * M : nullptr;
+        uint16_t *out = a.codes ? a.codes + c * M : nullptr;
+        if (a.oscale) a.oscale[c] = (uint8_t)oscale;
         if (a.o_oscale) { a.o_oscale[c] = oscale; a.o_tableID[c] = tid; }
         for (int bd = 0; bd < NB && !bad; bd++) {
             int ba = (int)r.get(a.nMantSizeBits);                     // :195
             if (ba) ba += 1;                                          // :196
             const int sf = (int)r.get(a.nScaleBits);                  // :198
+            if (a.meta) a.meta[c * kMaxBands + bd] = (uint16_t)(sf | (ba << 8));
             if (a.o_ba) { a.o_ba[c * kMaxBands + bd] = ba; a.o_sf[c * kMaxBands + bd] = sf; }
             const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
             if (!ba) {
-                for (int i = lo; i < hi; i++) { if (out) out[i] = (T)0; if (a.o_mant) a.o_mant[c * M + i] = 0; }
+                if (a.o_mant) for (int i = lo; i < hi; i++) a.o_mant[c * M + i] = 0;
                 continue;
             }
-            const int64_t signPos = r.pos;                            // nLines sign bits first (:202-204)
-            r.pos += hi - lo;
+            BitReader sr = r;                                         // nLines sign bits first (:202-204) ...
+            r.seek(p, r.used + (hi - lo));                            // ... then the codes
+            const uint32_t signBit = 1u << (ba - 1);
             for (int i = lo; i < hi; i++) {
+                r.fill();
                 uint32_t e = lut[r.peek(kLutBits)];
                 int sym;
-                if (e & kLutLeaf) { r.pos += e & 0xff; sym = (int)((e >> 8) & 0x7fffff) - 1; }
+                if (e & kLutLeaf) { r.skip((int)(e & 0xff)); sym = (int)((e >> 8) & 0x7fffff) - 1; }
                 else if (e == kLutInvalid) { bad = true; break; }
                 else {                                                // long code: continue bit-serially (Huffman.py:337-344)
                     int node = (int)e;
-                    r.pos += kLutBits;
+                    r.skip(kLutBits);
                     while (a.dt.sym[node] == -2) {
                         node = a.dt.child[2 * node + (int)r.get(1)];
-                        if (node < 0 || r.pos > r.nbits) { bad = true; break; }
+                        if (node < 0 || r.used > r.nbits) { bad = true; break; }
                     }
                     if (bad) break;
                     sym = a.dt.sym[node];
                 }
-                long long m = sym < 0 ? (long long)r.get(ba) : (long long)sym;    // escape: Huffman.py:326-327
-                BitReader sr = r;
-                sr.pos = signPos + (i - lo);
-                if (sr.peek(1)) m += 1ll << (ba - 1);                 // pacfile.py:210
+                uint32_t m = sym < 0 ? r.get(ba) : (uint32_t)sym;     // escape: Huffman.py:326-327
+                if (sr.get(1)) m += signBit;                          // pacfile.py:210
+                if (m > 0xffffu) { bad = true; break; }               // no ba <= 16 code is that large
                 if (a.o_mant) a.o_mant[c * M + i] = (int32_t)m;
-                if (out) out[i] = (T)(dequant(sf, m, largestScale, ba) * rescale);
+                if (out) out[i] = (uint16_t)m;
             }
         }
         uint32_t lr = 0;
         for (int bd = 0; bd < NB; bd++) lr |= r.get(1) << bd;         // :216-217
-        if (r.pos > r.nbits) bad = true;
+        if (r.used > r.nbits) bad = true;
         if ((c & 1) == 1) a.lrms[w] = lr;                             // the last channel's copy wins
         if (bad && a.err) a.err[s] = PAC_E_FORMAT;
     }
@@ -171,7 +222,11 @@ __global__ void k_unpack(const UnpackArgs<T> a) {
 // ---------------------------------------------------------------- K7: synthesis
 template <typename T>
 struct SynthArgs {
-    const T *lines;              // [S][maxBlocks][2][M] dequantised (pre M/S recombination)
+    const T *lines;              // [S][maxBlocks][2][M] dequantised (pre M/S recombination), or NULL and instead:
+    const uint16_t *codes;       // [chunk][M]  k_unpack's mantissa codes
+    const uint16_t *meta;        // [chunk][kMaxBands] sf | ba << 8
+    const uint8_t *oscale;       // [chunk]
+    int largestScale;            // (1 << nScaleBits) - 1
     const uint32_t *lrms;        // [S][maxBlocks]
     const int32_t *nBlocks;      // [S]
     int S, maxBlocks, run;       // each CTA produces `run` consecutive output blocks of one stream
@@ -191,6 +246,7 @@ struct SynthSmem {
     T2 W[2][M / 2 + 2];
     T y[2][2 * M];
     T ola[2][M];
+    uint16_t meta[2][kMaxBands];
 };
 
 // PCMFile.WriteDataBlock quantisation (pcmfile.py:127-134, quantize.py:91-117 with 16 bits)
@@ -226,13 +282,31 @@ k_synth(const SynthArgs<T> a) {
     for (int b = bFirst; b <= bLast; b++) {
         const int64_t w = (int64_t)s * a.maxBlocks + b;
         const uint32_t lrms = a.lrms[w];
-        // load + M/S recombination with the reference's aliasing (codec.py:46-56): L' = M - S, R' = L' + S
+        // load (+ dequantise, codec.py:31-43) + M/S recombination with the reference's aliasing (codec.py:46-56):
+        // L' = M - S, R' = L' + S
+        if (a.codes) {
+            if (tid < 2 * kMaxBands) sm.meta[tid / kMaxBands][tid % kMaxBands] = a.meta[w * 2 * kMaxBands + tid];
+            __syncthreads();
+            const double r0 = 1.0 / (double)(1 << a.oscale[w * 2]), r1 = 1.0 / (double)(1 << a.oscale[w * 2 + 1]);   // exact powers of two
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int i = tid + NT * j;
-            T x0 = a.lines[(w * 2 + 0) * M + i], x1 = a.lines[(w * 2 + 1) * M + i];
-            if ((lrms >> tb.band_of_line[i]) & 1u) { x0 = x0 - x1; x1 = x0 + x1; }
-            sm.X[0][i] = x0; sm.X[1][i] = x1;
+            for (int j = 0; j < 4; j++) {
+                int i = tid + NT * j;
+                int bd = tb.band_of_line[i];
+                uint32_t m0 = sm.meta[0][bd], m1 = sm.meta[1][bd];
+                T x0 = (T)0, x1 = (T)0;
+                if (m0 >> 8) x0 = (T)(dequant((int)(m0 & 0xff), (long long)a.codes[(w * 2 + 0) * M + i], a.largestScale, (int)(m0 >> 8)) * r0);
+                if (m1 >> 8) x1 = (T)(dequant((int)(m1 & 0xff), (long long)a.codes[(w * 2 + 1) * M + i], a.largestScale, (int)(m1 >> 8)) * r1);
+                if ((lrms >> bd) & 1u) { x0 = x0 - x1; x1 = x0 + x1; }
+                sm.X[0][i] = x0; sm.X[1][i] = x1;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int i = tid + NT * j;
+                T x0 = a.lines[(w * 2 + 0) * M + i], x1 = a.lines[(w * 2 + 1) * M + i];
+                if ((lrms >> tb.band_of_line[i]) & 1u) { x0 = x0 - x1; x1 = x0 + x1; }
+                sm.X[0][i] = x0; sm.X[1][i] = x1;
+            }
         }
         __syncthreads();
         // DCT-IV by fold + M/2-point FFT (same routine as the forward MDCT)

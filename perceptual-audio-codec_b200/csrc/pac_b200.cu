@@ -938,8 +938,8 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
         if (pacLen[s] < hdrB) FAIL(PAC_E_FORMAT, "stream %d shorter than a PAC header", s);
         if (pacLen[s] > maxLenAll) maxLenAll = pacLen[s];
     }
-    // stream groups keep the dequantised-lines intermediate bounded (~8 GB)
-    const int64_t perStream = ((maxLenAll - hdrB) / minBlock + 1) * 2 * M * (int64_t)sizeof(T);
+    // stream groups keep the mantissa-code intermediate bounded (~8 GB)
+    const int64_t perStream = ((maxLenAll - hdrB) / minBlock + 1) * 2 * M * (int64_t)sizeof(uint16_t);
     int Sg = (int)(((int64_t)8 << 30) / (perStream > 0 ? perStream : 1));
     if (Sg < 1) Sg = 1;
     if (Sg > S) Sg = S;
@@ -997,7 +997,7 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
         ia.pac = d_pac; ia.pacBeg = d_beg; ia.pacLen = d_len; ia.S = Sc; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
         ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
         ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
-        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(Sc + 127) / 128, 128, 0, ctx->stream>>>(ia); }
+        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(Sc + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ia); }
         ctx->launches++;
         CK(cudaGetLastError());
         std::vector<int32_t> nblk(Sc), stt(Sc);
@@ -1008,15 +1008,18 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
             if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s0 + s);   // pacfile.py:184
             if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s0 + s, (long long)nblk[s] * M);
         }
-        // ---- unpack + dequantise
-        CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(T)));
+        // ---- unpack (dequantisation happens in the synthesis kernel, all threads in parallel)
+        CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(uint16_t)));
+        CK(ctx->w_ba.ensure((size_t)nblkAll * 2 * kMaxBands * sizeof(uint16_t)));
+        CK(ctx->w_sf.ensure((size_t)nblkAll * 2));
         CK(ctx->w_lrms.ensure((size_t)nblkAll * 4));
         CK(cudaMemsetAsync(ctx->w_misc3.p, 0, (size_t)Sc * 4, ctx->stream));
         UnpackArgs<T> ua{};
         ua.pac = d_pac; ua.chunkPos = ia.chunkPos; ua.chunkLen = ia.chunkLen; ua.nBlocks = ia.nBlocks;
         ua.S = Sc; ua.maxBlocks = maxBlocks; ua.M = M;
         ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;   // pacfile.py:189
-        ua.lines = ctx->w_lines.as<T>(); ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
+        ua.codes = ctx->w_lines.as<uint16_t>(); ua.meta = ctx->w_ba.as<uint16_t>(); ua.oscale = ctx->w_sf.as<uint8_t>();
+        ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
         ua.dt = ctx->dt; ua.bands = ctx->bands;
         {
             int64_t nchunk = nblkAll * 2;
@@ -1032,7 +1035,8 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
         else { CK(ctx->w_pcm.ensure((size_t)Sc * stride * 4)); d_pcm = ctx->w_pcm.as<int16_t>(); }
         CK(ctx->w_misc4.ensure((size_t)Sc * 8));
         SynthArgs<T> sa{};
-        sa.lines = ua.lines; sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = Sc; sa.maxBlocks = maxBlocks; sa.run = 16;
+        sa.lines = nullptr; sa.codes = ua.codes; sa.meta = ua.meta; sa.oscale = ua.oscale; sa.largestScale = (1 << ctx->p.nScaleBits) - 1;
+        sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = Sc; sa.maxBlocks = maxBlocks; sa.run = 16;
         sa.pcm = d_pcm; sa.strideSamples = stride; sa.nSamplesOut = ctx->w_misc4.as<int64_t>(); sa.rawOut = nullptr;
         int runsPerStream = (maxBlocks + sa.run) / sa.run;
         int rc = launch_synth<T>(ctx, sa, (int64_t)Sc * runsPerStream);
@@ -1244,7 +1248,7 @@ extern "C" int pac_unpack_blocks(PacCtx *ctx, const uint8_t *chunks, int64_t chu
     ua.pac = ctx->w_misc.as<uint8_t>(); ua.chunkPos = ctx->w_coff.as<int64_t>(); ua.chunkLen = ctx->w_nby.as<int32_t>(); ua.nBlocks = nullptr;
     ua.S = 1; ua.maxBlocks = nblk; ua.M = M;
     ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;
-    ua.lines = nullptr; ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_ovf.as<int32_t>();
+    ua.codes = nullptr; ua.meta = nullptr; ua.oscale = nullptr; ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_ovf.as<int32_t>();
     ua.o_sf = ctx->w_misc2.as<int32_t>(); ua.o_ba = ctx->w_misc3.as<int32_t>(); ua.o_mant = ctx->w_misc4.as<int32_t>();
     ua.o_oscale = ctx->w_misc5.as<int32_t>(); ua.o_tableID = ctx->w_misc6.as<int32_t>();
     ua.dt = ctx->dt; ua.bands = ctx->bands;
