@@ -26,7 +26,7 @@ struct IndexArgs {
     const int64_t *pacBeg;      // [S] first byte of each stream's file image
     const int64_t *pacLen;      // [S] its length
     int S, hdrBytes, maxBlocks;
-    int64_t *chunkPos;          // [S][maxBlocks][2] absolute byte offset of each payload
+    int64_t *chunkPos;          // [S][maxBlocks][2] absolute byte offset of each payload (NULL: count blocks only)
     int32_t *chunkLen;          // [S][maxBlocks][2]
     int32_t *nBlocks;           // [S]
     int32_t *status;            // [S] 0 ok, PAC_E_FORMAT on a truncated chunk
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(32 * kIdxWarps) k_index(const IndexArgs a) {
         if (pos + 4 > end) break;                         // EOF on the second channel: block is dropped
         n1 = rd(pos); p1 = pos + 4; pos = p1 + n1;
         if (pos > end) { st = PAC_E_FORMAT; break; }
-        if (lane == 0) {
+        if (lane == 0 && a.chunkPos) {
             int64_t o = ((int64_t)s * a.maxBlocks + nb) * 2;
             *reinterpret_cast<longlong2 *>(a.chunkPos + o) = make_longlong2(p0, p1);
             *reinterpret_cast<int2 *>(a.chunkLen + o) = make_int2((int)n0, (int)n1);
@@ -95,40 +95,38 @@ __global__ void k_gather_headers(const uint8_t *pac, const int64_t *pacBeg, int 
 }
 
 // ---------------------------------------------------------------- K6b: one thread parses one channel chunk
-// MSB-first bit reader (bitpack.py:104-170) over global memory: a 64-bit window, topped up with aligned, clamped
-// 32-bit loads.  Reading past the chunk returns repeated bytes; `used > nbits` flags it afterwards.
+// MSB-first bit reader (bitpack.py:104-170) over global memory: the 32-bit word holding the current bit, the next
+// one and a prefetched third (its load latency hides behind the 32 bits in front of it); aligned, clamped loads.
+// Reading past the chunk returns repeated bytes; `used > nbits` flags it afterwards.
 struct BitReader {
     const uint32_t *wp, *wlast;
-    uint64_t buf;
-    int cnt;                     // valid bits at the top of buf
-    int64_t used, nbits;
+    uint32_t w0, w1, w2;
+    int bp;                      // bit offset of the cursor inside w0
+    int used, nbits;
     __device__ __forceinline__ uint32_t word() {
         uint32_t v = __ldg(wp < wlast ? wp : wlast);
         wp++;
         return __byte_perm(v, 0, 0x0123);
     }
-    __device__ __forceinline__ void seek(const uint8_t *p, int64_t bitpos) {
+    __device__ __forceinline__ void seek(const uint8_t *p, int bitpos) {
         uintptr_t A = (uintptr_t)p + (uintptr_t)(bitpos >> 3);
         wp = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);
-        int off = (int)(A & 3) * 8 + (int)(bitpos & 7);
-        uint64_t hi = word(), lo = word();
-        buf = ((hi << 32) | lo) << off;
-        cnt = 64 - off;
+        bp = (int)(A & 3) * 8 + (bitpos & 7);
+        w0 = word(); w1 = word(); w2 = word();
         used = bitpos;
     }
-    __device__ __forceinline__ void init(const uint8_t *p, int64_t nbytes) {
+    __device__ __forceinline__ void init(const uint8_t *p, int nbytes) {
         nbits = nbytes * 8;
         wlast = reinterpret_cast<const uint32_t *>(((uintptr_t)p + (uintptr_t)(nbytes > 0 ? nbytes - 1 : 0)) & ~(uintptr_t)3);
         seek(p, 0);
     }
-    __device__ __forceinline__ void fill() {              // afterwards cnt >= 33
-        if (cnt <= 32) { buf |= (uint64_t)word() << (32 - cnt); cnt += 32; }
+    __device__ __forceinline__ uint32_t peek(int n) { return __funnelshift_l(w1, w0, bp) >> (32 - n); }     // 1 <= n <= 32
+    __device__ __forceinline__ void skip(int n) {                                                           // 0 <= n <= 32
+        bp += n; used += n;
+        if (bp >= 32) { bp -= 32; w0 = w1; w1 = w2; w2 = word(); }
     }
-    __device__ __forceinline__ uint32_t peek(int n) { return (uint32_t)(buf >> (64 - n)); }     // 1 <= n <= 32, after fill()
-    __device__ __forceinline__ void skip(int n) { buf <<= n; cnt -= n; used += n; }
-    __device__ __forceinline__ uint32_t get(int n) {      // 0 <= n <= 32
+    __device__ __forceinline__ uint32_t get(int n) {
         if (!n) return 0;
-        fill();
         uint32_t v = peek(n);
         skip(n);
         return v;
@@ -144,7 +142,7 @@ struct UnpackArgs {
     int S, maxBlocks, M;
     int nScaleBits, nMantSizeBits, nTableIDBits;
     // outputs, chunk-indexed c = (s*maxBlocks + b)*2 + ch
-    uint16_t *codes;             // [nchunk][M] mantissa codes, sign at bit ba-1 (lines of zero-bit bands are NOT written)
+    uint16_t *codes;             // [nchunk][M] mantissa codes, sign at bit ba-1 (lines of zero-bit bands may be left unwritten)
     uint16_t *meta;              // [nchunk][kMaxBands] sf | ba << 8
     uint8_t *oscale;             // [nchunk]
     uint32_t *lrms;              // [nblocks] (from the LAST channel parsed, pacfile.py:216-217)
@@ -154,8 +152,26 @@ struct UnpackArgs {
     BandInfo bands;
 };
 
+// Collects a chunk's codes in line order and writes them 8 at a time (one 16 B store): a thread owns a whole 2 KB row,
+// so 2-byte stores would cost one L2 sector write each.
+struct CodeSink {
+    uint16_t *row;
+    uint4 q;
+    uint32_t cur;
+    __device__ __forceinline__ void push(uint32_t v, int i) {
+        if (i & 1) {
+            q.x = q.y; q.y = q.z; q.z = q.w; q.w = cur | (v << 16);
+            if ((i & 7) == 7) *reinterpret_cast<uint4 *>(row + i - 7) = q;
+        } else cur = v;
+    }
+};
+
+constexpr int kUnpackThreads = 128;
+
+// (The first-level tables stay in global memory: a shared-memory copy (40 KB) cost more in occupancy and L1 capacity
+// than it saved in lookup latency -- 52.6 vs 26.7 ms on the 1024 x 60 s corpus.)
 template <typename T>
-__global__ void __launch_bounds__(64) k_unpack(const UnpackArgs<T> a) {
+__global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a) {
     const int64_t nchunk = (int64_t)a.S * a.maxBlocks * 2;
     const int NB = a.bands.nBands, M = a.M;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (int64_t)gridDim.x * blockDim.x) {
@@ -171,7 +187,9 @@ __global__ void __launch_bounds__(64) k_unpack(const UnpackArgs<T> a) {
         const int tid = (int)r.get(a.nTableIDBits);                   // :190
         bad |= tid < 1 || tid > kNTables;
         const uint32_t *lut = a.dt.lut + (size_t)(bad ? 0 : tid - 1) * (1 << kLutBits);
-        uint16_t *out = a.codes ? a.codes + c * M : nullptr;
+        CodeSink sink;
+        sink.row = a.codes ? a.codes + c * M : nullptr;
+        sink.q = make_uint4(0, 0, 0, 0); sink.cur = 0;
         if (a.oscale) a.oscale[c] = (uint8_t)oscale;
         if (a.o_oscale) { a.o_oscale[c] = oscale; a.o_tableID[c] = tid; }
         for (int bd = 0; bd < NB && !bad; bd++) {
@@ -183,13 +201,18 @@ __global__ void __launch_bounds__(64) k_unpack(const UnpackArgs<T> a) {
             const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
             if (!ba) {
                 if (a.o_mant) for (int i = lo; i < hi; i++) a.o_mant[c * M + i] = 0;
+                if (sink.row) {                                       // keep the 8-line groups that straddle the band edges whole;
+                    int i = lo;                                       // groups entirely inside a zero-bit band are never read
+                    for (; i < hi && (i & 7); i++) sink.push(0, i);
+                    i += (hi - i) & ~7;
+                    for (; i < hi; i++) sink.push(0, i);
+                }
                 continue;
             }
             BitReader sr = r;                                         // nLines sign bits first (:202-204) ...
             r.seek(p, r.used + (hi - lo));                            // ... then the codes
             const uint32_t signBit = 1u << (ba - 1);
             for (int i = lo; i < hi; i++) {
-                r.fill();
                 uint32_t e = lut[r.peek(kLutBits)];
                 int sym;
                 if (e & kLutLeaf) { r.skip((int)(e & 0xff)); sym = (int)((e >> 8) & 0x7fffff) - 1; }
@@ -208,7 +231,7 @@ __global__ void __launch_bounds__(64) k_unpack(const UnpackArgs<T> a) {
                 if (sr.get(1)) m += signBit;                          // pacfile.py:210
                 if (m > 0xffffu) { bad = true; break; }               // no ba <= 16 code is that large
                 if (a.o_mant) a.o_mant[c * M + i] = (int32_t)m;
-                if (out) out[i] = (uint16_t)m;
+                if (sink.row) sink.push(m, i);
             }
         }
         uint32_t lr = 0;
@@ -242,11 +265,10 @@ template <typename T, int LOGM>
 struct SynthSmem {
     static constexpr int M = 1 << LOGM;
     using T2 = typename Vec2<T>::type;
-    T X[2][M];
-    T2 W[2][M / 2 + 2];
-    T y[2][2 * M];
-    T ola[2][M];
+    T2 W[2][M / 2 + 2];          // folded spectrum / FFT workspace
+    T v[2][M];                   // DCT-IV output
     uint16_t meta[2][kMaxBands];
+    float gain[2][kMaxBands];    // fp32 mode: 2/(2^R-1) * 2^(largestScale-sf-1-overallScale) per band
 };
 
 // PCMFile.WriteDataBlock quantisation (pcmfile.py:127-134, quantize.py:91-117 with 16 bits)
@@ -254,6 +276,32 @@ __device__ __forceinline__ int pcm16(double v) {
     double a = fabs(v);
     int code = a < 1.0 ? (int)((a * 65535.0 + 1.0) / 2.0) : 32767;
     return signbit(v) ? -code : code;
+}
+__device__ __forceinline__ int pcm16(float v) {          // fp32 mode: within 1 LSB of the above
+    float a = fabsf(v);
+    int code = a < 1.0f ? (int)(a * 32767.5f + 0.5f) : 32767;
+    return signbit(v) ? -code : code;
+}
+
+// one dequantised line (codec.py:31-43, quantize.py:345-376)
+template <typename T, typename SS>
+__device__ __forceinline__ T synth_line(const SynthArgs<T> &a, const SS &sm, int64_t chunk, int ch, int i, int bd, double rescale) {
+    if (!a.codes) return a.lines[chunk * SS::M + i];
+    const uint32_t mt = sm.meta[ch][bd];
+    const int ba = (int)(mt >> 8), sf = (int)(mt & 0xff);
+    if (!ba) return (T)0;
+    const uint32_t code = a.codes[chunk * SS::M + i];
+    if constexpr (sizeof(T) == 8) {
+        return (T)(dequant(sf, (long long)code, a.largestScale, ba) * rescale);
+    } else {
+        const uint32_t signMask = 1u << (ba - 1);
+        const bool neg = (code & signMask) != 0;
+        const uint32_t mag = neg ? code - signMask : code;
+        // q = mag << (L - sf) (+ half a step)  =  (2 mag + 1) * 2^(L-sf-1), exact in fp32; the power of two lives in gain[]
+        const float q = (float)(int)(2u * mag + ((sf < a.largestScale && mag > 0) ? 1u : 0u));
+        const float x = q * sm.gain[ch][bd];
+        return neg ? -x : x;
+    }
 }
 
 template <typename T, int LOGM>
@@ -279,77 +327,90 @@ k_synth(const SynthArgs<T> a) {
     else { j0 = r * a.run; j1 = min(j0 + a.run, nblk); if (j0 >= nblk) { return; } }
     if (!a.rawOut && r == 0 && tid == 0) a.nSamplesOut[s] = (int64_t)nblk * M;
     const int bFirst = j0, bLast = a.rawOut ? j0 : min(j1, nblk - 1);    // decoded blocks needed: j0 .. j1 (clipped)
+    T ola[4][2];                                                         // overlap tail of samples tid + NT*j (this thread's own)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ola[j][0] = ola[j][1] = (T)0;
     for (int b = bFirst; b <= bLast; b++) {
         const int64_t w = (int64_t)s * a.maxBlocks + b;
         const uint32_t lrms = a.lrms[w];
-        // load (+ dequantise, codec.py:31-43) + M/S recombination with the reference's aliasing (codec.py:46-56):
-        // L' = M - S, R' = L' + S
+        double r0 = 1.0, r1 = 1.0;
         if (a.codes) {
-            if (tid < 2 * kMaxBands) sm.meta[tid / kMaxBands][tid % kMaxBands] = a.meta[w * 2 * kMaxBands + tid];
+            if (tid < 2 * kMaxBands) {
+                const int ch = tid / kMaxBands, bd = tid % kMaxBands;
+                const uint32_t mt = a.meta[w * 2 * kMaxBands + tid];
+                sm.meta[ch][bd] = (uint16_t)mt;
+                if (sizeof(T) == 4) {
+                    const int ba = (int)(mt >> 8), sf = (int)(mt & 0xff);
+                    const double largest = (double)(1ll << ((ba + a.largestScale) & 63)) - 1.0;
+                    sm.gain[ch][bd] = (float)ldexp(2.0 / largest, a.largestScale - sf - 1 - (int)a.oscale[w * 2 + ch]);
+                }
+            }
+            r0 = 1.0 / (double)(1 << a.oscale[w * 2]); r1 = 1.0 / (double)(1 << a.oscale[w * 2 + 1]);   // exact powers of two
             __syncthreads();
-            const double r0 = 1.0 / (double)(1 << a.oscale[w * 2]), r1 = 1.0 / (double)(1 << a.oscale[w * 2 + 1]);   // exact powers of two
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int i = tid + NT * j;
-                int bd = tb.band_of_line[i];
-                uint32_t m0 = sm.meta[0][bd], m1 = sm.meta[1][bd];
-                T x0 = (T)0, x1 = (T)0;
-                if (m0 >> 8) x0 = (T)(dequant((int)(m0 & 0xff), (long long)a.codes[(w * 2 + 0) * M + i], a.largestScale, (int)(m0 >> 8)) * r0);
-                if (m1 >> 8) x1 = (T)(dequant((int)(m1 & 0xff), (long long)a.codes[(w * 2 + 1) * M + i], a.largestScale, (int)(m1 >> 8)) * r1);
-                if ((lrms >> bd) & 1u) { x0 = x0 - x1; x1 = x0 + x1; }
-                sm.X[0][i] = x0; sm.X[1][i] = x1;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int i = tid + NT * j;
-                T x0 = a.lines[(w * 2 + 0) * M + i], x1 = a.lines[(w * 2 + 1) * M + i];
-                if ((lrms >> tb.band_of_line[i]) & 1u) { x0 = x0 - x1; x1 = x0 + x1; }
-                sm.X[0][i] = x0; sm.X[1][i] = x1;
-            }
         }
-        __syncthreads();
-        // DCT-IV by fold + M/2-point FFT (same routine as the forward MDCT)
-        for (int e = tid; e < 2 * H; e += NT) {
-            int ch = e / H, n = e - ch * H;
-            sm.W[ch][n] = cmul(mk2<T>(sm.X[ch][2 * n], sm.X[ch][M - 1 - 2 * n]), tb.mdct_pre[n]);
+        // load (+ dequantise) + M/S recombination with the reference's aliasing (codec.py:46-56: L' = M - S,
+        // R' = L' + S), folded straight into the DCT-IV pre-twiddle: W[n] = (X[2n] + i X[M-1-2n]) e^{-i pi n/M}
+        for (int n = tid; n < H; n += NT) {
+            const int iA = 2 * n, iB = M - 1 - 2 * n;
+            const int bA = tb.band_of_line[iA], bB = tb.band_of_line[iB];
+            T a0 = synth_line<T, SS>(a, sm, w * 2, 0, iA, bA, r0), a1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iA, bA, r1);
+            T b0 = synth_line<T, SS>(a, sm, w * 2, 0, iB, bB, r0), b1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iB, bB, r1);
+            if ((lrms >> bA) & 1u) { a0 = a0 - a1; a1 = a0 + a1; }
+            if ((lrms >> bB) & 1u) { b0 = b0 - b1; b1 = b0 + b1; }
+            const T2 pre = tb.mdct_pre[n];
+            sm.W[0][n] = cmul(mk2<T>(a0, b0), pre);
+            sm.W[1][n] = cmul(mk2<T>(a1, b1), pre);
         }
         __syncthreads();
         fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, H + 2, tb.tw, 2);
         for (int e = tid; e < 2 * H; e += NT) {
             int ch = e / H, k = e - ch * H;
             T2 yv = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
-            sm.X[ch][2 * k] = yv.x;                 // v[2k]
-            sm.X[ch][M - 1 - 2 * k] = -yv.y;        // v[M-1-2k]
+            sm.v[ch][2 * k] = yv.x;                 // v[2k]
+            sm.v[ch][M - 1 - 2 * k] = -yv.y;        // v[M-1-2k]
         }
         __syncthreads();
-        // unfold (IMDCT, mdct.py:73-80: y[n] = 2 sum_k X[k] cos(2pi/N (n+n0)(k+1/2))) and SineWindow (codec.py:59-60)
-        for (int e = tid; e < 2 * N; e += NT) {
-            int ch = e / N, n = e - ch * N;
-            T v = n < H ? sm.X[ch][n + H] : (n < 3 * H ? -sm.X[ch][3 * H - 1 - n] : -sm.X[ch][n - 3 * H]);
-            sm.y[ch][n] = (T)2 * v * tb.sinw[n];
-        }
-        __syncthreads();
-        if (a.rawOut) {
-            for (int e = tid; e < 2 * N; e += NT) a.rawOut[(int64_t)blockIdx.x * 2 * N + e] = (double)sm.y[e / N][e % N];
-            return;
-        }
-        // overlap-add (pacfile.py:223-226) and PCM quantisation; output block index = b - 1
-        if (b > j0) {
-            int16_t *dst = a.pcm + ((int64_t)s * a.strideSamples + (int64_t)(b - 1) * M) * 2;
-            for (int e = tid; e < 2 * M; e += NT) {
-                int i = e >> 1, ch = e & 1;
-                dst[e] = (int16_t)pcm16((double)sm.ola[ch][i] + (double)sm.y[ch][i]);
+        // unfold (IMDCT, mdct.py:73-80: y[n] = 2 sum_k X[k] cos(2pi/N (n+n0)(k+1/2))), SineWindow (codec.py:59-60),
+        // overlap-add (pacfile.py:223-226) and PCM quantisation in one pass; output block index = b - 1
+        int16_t *dst = a.rawOut ? nullptr : a.pcm + ((int64_t)s * a.strideSamples + (int64_t)(b - 1) * M) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = tid + NT * j;
+            const int iF = i < H ? i + H : 3 * H - 1 - i;      // y[i]   =  v[i+H] | -v[3H-1-i]
+            const int iS = i < H ? H - 1 - i : i - H;          // y[M+i] = -v[H-1-i] | -v[i-H]
+            const T wF = tb.sinw[i], wS = tb.sinw[M + i];
+            short2 o;
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                T vF = sm.v[ch][iF], vS = -sm.v[ch][iS];
+                if (i >= H) vF = -vF;
+                const T yF = (T)2 * vF * wF, yS = (T)2 * vS * wS;
+                if (a.rawOut) {
+                    a.rawOut[((int64_t)blockIdx.x * 2 + ch) * N + i] = (double)yF;
+                    a.rawOut[((int64_t)blockIdx.x * 2 + ch) * N + M + i] = (double)yS;
+                } else {
+                    int q;
+                    if constexpr (sizeof(T) == 8) q = pcm16((double)ola[j][ch] + (double)yF);
+                    else q = pcm16(ola[j][ch] + yF);
+                    if (ch == 0) o.x = (short)q; else o.y = (short)q;
+                    ola[j][ch] = yS;
+                }
             }
+            if (!a.rawOut && b > j0) *reinterpret_cast<short2 *>(dst + 2 * i) = o;
         }
-        __syncthreads();
-        for (int e = tid; e < 2 * M; e += NT) sm.ola[e / M][e % M] = sm.y[e / M][M + e % M];
-        __syncthreads();
+        // no barrier needed here: the next block's load phase only writes W, and v is rewritten after the FFT's barriers
     }
     // the tail block (EOF): only the CTA whose range reaches the end emits it
-    if (j1 == nblk) {
+    if (!a.rawOut && j1 == nblk) {
         int16_t *dst = a.pcm + ((int64_t)s * a.strideSamples + (int64_t)(nblk - 1) * M) * 2;
-        for (int e = tid; e < 2 * M; e += NT) dst[e] = (int16_t)pcm16((double)sm.ola[e & 1][e >> 1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = tid + NT * j;
+            short2 o;
+            if constexpr (sizeof(T) == 8) { o.x = (short)pcm16((double)ola[j][0]); o.y = (short)pcm16((double)ola[j][1]); }
+            else { o.x = (short)pcm16(ola[j][0]); o.y = (short)pcm16(ola[j][1]); }
+            *reinterpret_cast<short2 *>(dst + 2 * i) = o;
+        }
     }
 }
 

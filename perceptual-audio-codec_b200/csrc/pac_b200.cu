@@ -933,99 +933,101 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
     const int M = ctx->M, hdrB = header_bytes(ctx);
     const bool pacDev = is_device_ptr(pac), pcmDev = is_device_ptr(pcm);
     const int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
-    int64_t maxLenAll = 0;
-    for (int s = 0; s < S; s++) {
+    for (int s = 0; s < S; s++)
         if (pacLen[s] < hdrB) FAIL(PAC_E_FORMAT, "stream %d shorter than a PAC header", s);
-        if (pacLen[s] > maxLenAll) maxLenAll = pacLen[s];
+    // ---- input: device images are used in place; host images are packed into one staging buffer
+    const uint8_t *d_pac = pac;
+    std::vector<int64_t> beg(pacBeg, pacBeg + S), len(pacLen, pacLen + S);
+    int64_t maxLen = 0;
+    if (!pacDev) {
+        int64_t tot = 0;
+        for (int s = 0; s < S; s++) { beg[s] = tot; tot += (len[s] + 15) & ~(int64_t)15; }
+        CK(ctx->w_misc.ensure((size_t)tot + 16));
+        for (int s = 0; s < S; s++)
+            CK(cudaMemcpyAsync(ctx->w_misc.as<uint8_t>() + beg[s], pac + pacBeg[s], (size_t)len[s], cudaMemcpyHostToDevice, ctx->stream));
+        d_pac = ctx->w_misc.as<uint8_t>();
     }
-    // stream groups keep the mantissa-code intermediate bounded (~8 GB)
-    const int64_t perStream = ((maxLenAll - hdrB) / minBlock + 1) * 2 * M * (int64_t)sizeof(uint16_t);
-    int Sg = (int)(((int64_t)8 << 30) / (perStream > 0 ? perStream : 1));
-    if (Sg < 1) Sg = 1;
-    if (Sg > S) Sg = S;
+    for (int s = 0; s < S; s++) if (len[s] > maxLen) maxLen = len[s];
+    CK(ctx->w_ns.ensure((size_t)S * 16));
+    int64_t *d_beg = ctx->w_ns.as<int64_t>(), *d_len = d_beg + S;
+    CK(cudaMemcpyAsync(d_beg, beg.data(), (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_len, len.data(), (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // ---- headers (pacfile.py:123-151) and a first walk of every stream's chunk chain (counts blocks, finds truncation)
+    std::vector<uint8_t> hdr((size_t)S * hdrB);
+    std::vector<int32_t> nblk(S), stt(S);
+    CK(ctx->w_hdr.ensure(hdr.size()));
+    CK(ctx->w_misc2.ensure((size_t)S * 4));   // nBlocks
+    CK(ctx->w_misc3.ensure((size_t)S * 4));   // status
+    k_gather_headers<<<(unsigned)((hdr.size() + 255) / 256), 256, 0, ctx->stream>>>(d_pac, d_beg, S, hdrB, ctx->w_hdr.as<uint8_t>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    IndexArgs ia{};
+    ia.pac = d_pac; ia.pacBeg = d_beg; ia.pacLen = d_len; ia.S = S; ia.hdrBytes = hdrB;
+    ia.maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
+    ia.chunkPos = nullptr; ia.chunkLen = nullptr;
+    ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
+    { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(S + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ia); }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hdr.data(), ctx->w_hdr.p, hdr.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     auto rd32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
     auto rd16 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); };
+    int maxBlocks = 1;
+    for (int s = 0; s < S; s++) {
+        const uint8_t *h = hdr.data() + (size_t)s * hdrB;
+        if (memcmp(h, "PAC ", 4)) FAIL(PAC_E_FORMAT, "stream %d: Tried to read a non-PAC file into a PACFile object", s);   // pacfile.py:130
+        if ((int)rd16(h + 8) != 2 || (int)rd32(h + 14) != M || (int)rd16(h + 18) != ctx->p.nScaleBits ||
+            (int)rd16(h + 20) != ctx->p.nMantSizeBits || (int)rd32(h + 22) != ctx->bands.nBands)
+            FAIL(PAC_E_FORMAT, "stream %d: header does not match this context's coding parameters", s);
+        for (int b = 0; b < ctx->bands.nBands; b++)
+            if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s);
+        if (hdrSampleRate) hdrSampleRate[s] = (int32_t)rd32(h + 4);
+        if (hdrNumSamples) hdrNumSamples[s] = rd32(h + 10);
+        if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s);   // pacfile.py:184
+        if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s, (long long)nblk[s] * M);
+        if (nblk[s] > maxBlocks) maxBlocks = nblk[s];
+    }
+    // ---- stream groups keep the mantissa-code intermediate bounded (~8 GB)
+    const int64_t perStream = (int64_t)maxBlocks * 2 * M * (int64_t)sizeof(uint16_t);
+    int Sg = (int)(((int64_t)8 << 30) / perStream);
+    if (Sg < 1) Sg = 1;
+    if (Sg > S) Sg = S;
     for (int s0 = 0; s0 < S; s0 += Sg) {
         const int Sc = (S - s0 < Sg) ? S - s0 : Sg;
-        // ---- input: device images are used in place; host images are packed into a staging buffer
-        const uint8_t *d_pac;
-        std::vector<int64_t> beg(Sc), len(Sc);
-        int64_t maxLen = 0;
-        if (pacDev) {
-            d_pac = pac;
-            for (int s = 0; s < Sc; s++) { beg[s] = pacBeg[s0 + s]; len[s] = pacLen[s0 + s]; }
-        } else {
-            int64_t tot = 0;
-            for (int s = 0; s < Sc; s++) { beg[s] = tot; len[s] = pacLen[s0 + s]; tot += (len[s] + 15) & ~(int64_t)15; }
-            CK(ctx->w_misc.ensure((size_t)tot + 16));
-            for (int s = 0; s < Sc; s++)
-                CK(cudaMemcpyAsync(ctx->w_misc.as<uint8_t>() + beg[s], pac + pacBeg[s0 + s], (size_t)len[s], cudaMemcpyHostToDevice, ctx->stream));
-            d_pac = ctx->w_misc.as<uint8_t>();
-        }
-        for (int s = 0; s < Sc; s++) if (len[s] > maxLen) maxLen = len[s];
-        CK(ctx->w_ns.ensure((size_t)Sc * 16));
-        int64_t *d_beg = ctx->w_ns.as<int64_t>(), *d_len = d_beg + Sc;
-        CK(cudaMemcpyAsync(d_beg, beg.data(), (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_len, len.data(), (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
-        // ---- headers (pacfile.py:123-151): must describe this context's layout
-        std::vector<uint8_t> hdr((size_t)Sc * hdrB);
-        CK(ctx->w_hdr.ensure(hdr.size()));
-        k_gather_headers<<<(unsigned)((hdr.size() + 255) / 256), 256, 0, ctx->stream>>>(d_pac, d_beg, Sc, hdrB, ctx->w_hdr.as<uint8_t>());
-        ctx->launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(hdr.data(), ctx->w_hdr.p, hdr.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (int s = 0; s < Sc; s++) {
-            const uint8_t *h = hdr.data() + (size_t)s * hdrB;
-            if (memcmp(h, "PAC ", 4)) FAIL(PAC_E_FORMAT, "stream %d: Tried to read a non-PAC file into a PACFile object", s0 + s);   // pacfile.py:130
-            if ((int)rd16(h + 8) != 2 || (int)rd32(h + 14) != M || (int)rd16(h + 18) != ctx->p.nScaleBits ||
-                (int)rd16(h + 20) != ctx->p.nMantSizeBits || (int)rd32(h + 22) != ctx->bands.nBands)
-                FAIL(PAC_E_FORMAT, "stream %d: header does not match this context's coding parameters", s0 + s);
-            for (int b = 0; b < ctx->bands.nBands; b++)
-                if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s0 + s);
-            if (hdrSampleRate) hdrSampleRate[s0 + s] = (int32_t)rd32(h + 4);
-            if (hdrNumSamples) hdrNumSamples[s0 + s] = rd32(h + 10);
-        }
-        const int maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
-        // ---- index
+        // ---- chunk index of this group (second walk, now into exactly sized arrays)
         const int64_t nblkAll = (int64_t)Sc * maxBlocks;
         CK(ctx->w_coff.ensure((size_t)nblkAll * 2 * 8));
         CK(ctx->w_nby.ensure((size_t)nblkAll * 2 * 4));
-        CK(ctx->w_misc2.ensure((size_t)Sc * 4));   // nBlocks
-        CK(ctx->w_misc3.ensure((size_t)Sc * 4));   // status
-        IndexArgs ia{};
-        ia.pac = d_pac; ia.pacBeg = d_beg; ia.pacLen = d_len; ia.S = Sc; ia.hdrBytes = hdrB; ia.maxBlocks = maxBlocks;
-        ia.chunkPos = ctx->w_coff.as<int64_t>(); ia.chunkLen = ctx->w_nby.as<int32_t>();
-        ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
-        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(Sc + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ia); }
+        CK(ctx->w_misc5.ensure((size_t)Sc * 8));   // nBlocks, status of the second walk
+        IndexArgs ig = ia;
+        ig.pacBeg = d_beg + s0; ig.pacLen = d_len + s0; ig.S = Sc; ig.maxBlocks = maxBlocks;
+        ig.chunkPos = ctx->w_coff.as<int64_t>(); ig.chunkLen = ctx->w_nby.as<int32_t>();
+        ig.nBlocks = ctx->w_misc5.as<int32_t>(); ig.status = ig.nBlocks + Sc;
+        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(Sc + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ig); }
         ctx->launches++;
         CK(cudaGetLastError());
-        std::vector<int32_t> nblk(Sc), stt(Sc);
-        CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (int s = 0; s < Sc; s++) {
-            if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s0 + s);   // pacfile.py:184
-            if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s0 + s, (long long)nblk[s] * M);
-        }
         // ---- unpack (dequantisation happens in the synthesis kernel, all threads in parallel)
         CK(ctx->w_lines.ensure((size_t)nblkAll * 2 * M * sizeof(uint16_t)));
         CK(ctx->w_ba.ensure((size_t)nblkAll * 2 * kMaxBands * sizeof(uint16_t)));
         CK(ctx->w_sf.ensure((size_t)nblkAll * 2));
         CK(ctx->w_lrms.ensure((size_t)nblkAll * 4));
-        CK(cudaMemsetAsync(ctx->w_misc3.p, 0, (size_t)Sc * 4, ctx->stream));
+        CK(ctx->w_misc6.ensure((size_t)Sc * 4));
+        CK(cudaMemsetAsync(ctx->w_misc6.p, 0, (size_t)Sc * 4, ctx->stream));
         UnpackArgs<T> ua{};
-        ua.pac = d_pac; ua.chunkPos = ia.chunkPos; ua.chunkLen = ia.chunkLen; ua.nBlocks = ia.nBlocks;
+        ua.pac = d_pac; ua.chunkPos = ig.chunkPos; ua.chunkLen = ig.chunkLen; ua.nBlocks = ig.nBlocks;
         ua.S = Sc; ua.maxBlocks = maxBlocks; ua.M = M;
         ua.nScaleBits = ctx->p.nScaleBits; ua.nMantSizeBits = ctx->p.nMantSizeBits; ua.nTableIDBits = 4;   // pacfile.py:189
         ua.codes = ctx->w_lines.as<uint16_t>(); ua.meta = ctx->w_ba.as<uint16_t>(); ua.oscale = ctx->w_sf.as<uint8_t>();
-        ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc3.as<int32_t>();
+        ua.lrms = ctx->w_lrms.as<uint32_t>(); ua.err = ctx->w_misc6.as<int32_t>();
         ua.dt = ctx->dt; ua.bands = ctx->bands;
         {
             int64_t nchunk = nblkAll * 2;
-            int64_t grid = (nchunk + 63) / 64;
-            if (grid > (int64_t)ctx->numSMs * 32) grid = (int64_t)ctx->numSMs * 32;
-            { KTimer kt(ctx, PAC_K_UNPACK); k_unpack<T><<<(unsigned)grid, 64, 0, ctx->stream>>>(ua); }
+            int64_t grid = (nchunk + kUnpackThreads - 1) / kUnpackThreads;
+            if (grid > (int64_t)ctx->numSMs * 16) grid = (int64_t)ctx->numSMs * 16;
+            { KTimer kt(ctx, PAC_K_UNPACK); k_unpack<T><<<(unsigned)grid, kUnpackThreads, 0, ctx->stream>>>(ua); }
             ctx->launches++;
             CK(cudaGetLastError());
         }
@@ -1036,17 +1038,17 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
         CK(ctx->w_misc4.ensure((size_t)Sc * 8));
         SynthArgs<T> sa{};
         sa.lines = nullptr; sa.codes = ua.codes; sa.meta = ua.meta; sa.oscale = ua.oscale; sa.largestScale = (1 << ctx->p.nScaleBits) - 1;
-        sa.lrms = ua.lrms; sa.nBlocks = ia.nBlocks; sa.S = Sc; sa.maxBlocks = maxBlocks; sa.run = 16;
+        sa.lrms = ua.lrms; sa.nBlocks = ig.nBlocks; sa.S = Sc; sa.maxBlocks = maxBlocks; sa.run = 16;
         sa.pcm = d_pcm; sa.strideSamples = stride; sa.nSamplesOut = ctx->w_misc4.as<int64_t>(); sa.rawOut = nullptr;
         int runsPerStream = (maxBlocks + sa.run) / sa.run;
         int rc = launch_synth<T>(ctx, sa, (int64_t)Sc * runsPerStream);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(stt.data(), ctx->w_misc3.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(stt.data(), ctx->w_misc6.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         int64_t maxS = 0;
         for (int s = 0; s < Sc; s++) {
             if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: malformed chunk (bad table ID or code)", s0 + s);
-            nSamplesOut[s0 + s] = (int64_t)nblk[s] * M;
+            nSamplesOut[s0 + s] = (int64_t)nblk[s0 + s] * M;
             if (nSamplesOut[s0 + s] > maxS) maxS = nSamplesOut[s0 + s];
         }
         if (!pcmDev && maxS > 0)
@@ -1252,7 +1254,7 @@ extern "C" int pac_unpack_blocks(PacCtx *ctx, const uint8_t *chunks, int64_t chu
     ua.o_sf = ctx->w_misc2.as<int32_t>(); ua.o_ba = ctx->w_misc3.as<int32_t>(); ua.o_mant = ctx->w_misc4.as<int32_t>();
     ua.o_oscale = ctx->w_misc5.as<int32_t>(); ua.o_tableID = ctx->w_misc6.as<int32_t>();
     ua.dt = ctx->dt; ua.bands = ctx->bands;
-    k_unpack<double><<<(unsigned)((nchunk + 63) / 64), 64, 0, ctx->stream>>>(ua);
+    k_unpack<double><<<(unsigned)((nchunk + kUnpackThreads - 1) / kUnpackThreads), kUnpackThreads, 0, ctx->stream>>>(ua);
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<int32_t> hsf((size_t)nchunk * kMaxBands), hba((size_t)nchunk * kMaxBands);
