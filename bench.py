@@ -263,9 +263,10 @@ def main():
     # ---- decode-only throughput (BASELINE.json configs[4]): the coded images are decoded where pac_encode_batch left them
     dec = None
     if args.decode:
-        ob_h = counts[mine].cpu().numpy()
-        beg = np.arange(len(mine), dtype=np.int64) * cap
-        pcm_out = torch.empty(len(mine), nblk * 1024 + 1024, 2, dtype=torch.int16, device=dev)
+        Sd = min(len(mine), 1024)                         # bounded: the decoded PCM needs its own buffer next to the inputs
+        ob_h = counts[mine].cpu().numpy()[:Sd]
+        beg = np.arange(Sd, dtype=np.int64) * cap
+        pcm_out = torch.empty(Sd, nblk * 1024 + 1024, 2, dtype=torch.int16, device=dev)
         dstride = pcm_out.shape[1]
         for _ in range(2):
             ns, _, _ = eng.decode_batch_strided(out, beg, ob_h, pcm_out, dstride)
@@ -282,8 +283,13 @@ def main():
         dl = torch.tensor([d0.elapsed_time(d1) * 1e-3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dl, op=dist.ReduceOp.MAX)
-        dec = {"value": audio_s * args.steps / float(dl.item()), "unit": "audio-s/s", "ms_per_step": float(dl.item()) / args.steps * 1e3,
-               "samples_per_stream": int(ns[0]), "kernels_ms": {k: v[0] for k, v in tmd.items() if v[1]}}
+        sd_all = torch.tensor([Sd], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(sd_all)
+        dec = {"value": int(sd_all.item()) * args.seconds * args.steps / float(dl.item()), "unit": "audio-s/s",
+               "ms_per_step": float(dl.item()) / args.steps * 1e3, "streams": int(sd_all.item()), "samples_per_stream": int(ns[0]),
+               "input": "coded images left on the device by pac_encode_batch ([S][cap] strided), PCM written to device memory",
+               "kernels_ms": {k: v[0] for k, v in tmd.items() if v[1]}}
         del pcm_out
 
     # ---- e2e through the C ABI with pinned host buffers
