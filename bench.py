@@ -193,6 +193,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -355,7 +359,7 @@ def main():
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         if dec:
             line["decode"] = dec
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

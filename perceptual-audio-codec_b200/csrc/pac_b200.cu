@@ -735,6 +735,10 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         int64_t maxBlocks = 0;
         for (int s = 0; s < Sc; s++) { int64_t nb = pac_num_blocks(ctx, nSamples[s0 + s]); if (nb > maxBlocks) maxBlocks = nb; }
         int TB = (int)(workBudget / Sc);
+        {   // at least ~16 tiles: only the LAST tile's scan+pack is not hidden under the next tile's analysis
+            const int tbCap = (int)((maxBlocks + 15) / 16);
+            if (TB > tbCap) TB = tbCap;
+        }
         if (TB < 8) TB = 8;
         if (TB > maxBlocks) TB = (int)maxBlocks;
         if (trace) TB = (int)maxBlocks;                      // taps are copied out once per group
