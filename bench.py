@@ -45,7 +45,8 @@ def gen_streams(stream_ids, n, device):
     """int16 [len(ids)][n][2] on `device`.  Stream s is seeded with 0x50414300 + s ('PAC\\0' + id): 3-8 sinusoids
     (log-uniform 50 Hz..16 kHz, -30..-6 dBFS, independent L/R gains), Gaussian noise at -50..-25 dBFS (per-channel
     fraction random), Poisson(2/s) transients = 5 ms exponentially decaying noise bursts at -12..-3 dBFS; clipped and
-    rounded to int16."""
+    rounded to int16.  The bursts are rounded to integers BEFORE they are scattered in (integer atomics commute; float
+    atomics would make overlapping bursts depend on the order of arrival, i.e. the corpus would differ from run to run)."""
     import torch
     out = torch.empty(len(stream_ids), n, 2, dtype=torch.int16, device=device)
     t = torch.arange(n, device=device, dtype=torch.float32) / FS
@@ -67,10 +68,12 @@ def gen_streams(stream_ids, n, device):
         if nb > 0 and n > blen:
             pos = (u(nb) * (n - blen)).long()
             lvl = 10 ** (-(3 + 9 * u(nb)) / 20)
+        acc = (sig.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int32)
+        if nb > 0 and n > blen:
             burst = torch.randn(nb, blen, 2, device=device, generator=g) * decay[None, :, None] * lvl[:, None, None]
             idx = (pos[:, None] + torch.arange(blen, device=device)[None, :]).reshape(-1)
-            sig.index_add_(0, idx, burst.reshape(-1, 2))
-        out[j] = (sig.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16)
+            acc.index_add_(0, idx, (burst.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int32).reshape(-1, 2))
+        out[j] = acc.clamp(-32767, 32767).to(torch.int16)
     return out
 
 

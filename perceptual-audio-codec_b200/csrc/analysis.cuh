@@ -39,6 +39,7 @@ struct AnalysisArgs {
     DevTables<double> tabd;      // double tables: fp32 mode computes the MDCT in fp64 and splits Bark values hi+lo
     FastTables ft;               // fp32 mode only
     BandInfo bands;
+    uint32_t poisonOn, poison, smemWords;   // debugging aid (PAC_POISON_SMEM): refill shared memory before every block
 };
 
 // extra shared memory of the fp32 fast threshold evaluation
@@ -432,6 +433,13 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         const int s = (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
+        if (a.poisonOn) {             // results must not depend on what a previous block left in shared memory
+            __syncthreads();
+            for (uint32_t i = tid; i < a.smemWords; i += NT) reinterpret_cast<uint32_t *>(smem_raw)[i] = a.poison;
+            __syncthreads();
+            if (tid < 8) sm.P[M + tid] = 0;
+            __syncthreads();
+        }
         // ------------------------------------------------ A. load one 2048-sample stereo window
         if (a.pcm) {
             const int64_t ns = a.nSamples[s];

@@ -624,6 +624,8 @@ template <typename T, int LOGM>
 static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     size_t smem = sizeof(AnalysisSmem<T, LOGM, sizeof(T) == 4>);
     if (const char *ex = getenv("PAC_EXTRA_SMEM")) smem += (size_t)atoi(ex);      // occupancy experiments
+    a.poisonOn = 0; a.poison = 0; a.smemWords = (uint32_t)(sizeof(AnalysisSmem<T, LOGM, sizeof(T) == 4>) / 4);
+    if (const char *po = getenv("PAC_POISON_SMEM")) { a.poisonOn = 1; a.poison = (uint32_t)strtoul(po, nullptr, 16); }
     static bool configured[2] = {false, false};
     (void)configured;
     CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -739,6 +741,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             const int tbCap = (int)((maxBlocks + 15) / 16);
             if (TB > tbCap) TB = tbCap;
         }
+        if (const char *tbe = getenv("PAC_TILE_BLOCKS")) TB = atoi(tbe);          // tests: force a tiling
         if (TB < 8) TB = 8;
         if (TB > maxBlocks) TB = (int)maxBlocks;
         if (trace) TB = (int)maxBlocks;                      // taps are copied out once per group

@@ -371,6 +371,28 @@ def test_device_resident_encode_then_strided_decode(e64, oracle):
         np.testing.assert_array_equal(dec[s, :ns[s]], ref)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
+    """A stream's image must not depend on which streams share its batch, on the tile length (analysis of tile t+1
+    overlaps scan+pack of tile t on separate CUDA streams), or on what an earlier block left in shared memory
+    (PAC_POISON_SMEM refills it before every block).  BASELINE config 4: identical bytes for every sharding."""
+    eng = pb.Engine(0, prec)
+    S, n = 24, 6 * 44100
+    batch = np.stack([synth_pcm(500 + s, n, ("mix", "mono", "left", "anti")[s % 4]) for s in range(S)])
+    ref = eng.encode_batch(batch)
+    try:
+        for tb in ("8", "13", "100000"):
+            os.environ["PAC_TILE_BLOCKS"] = tb
+            assert eng.encode_batch(batch) == ref, tb
+            assert eng.encode_batch(batch[5::2]) == ref[5::2], tb
+        for pat in ("0", "ffffffff", "7f7f7f7f"):
+            os.environ["PAC_POISON_SMEM"] = pat
+            assert eng.encode_batch(batch) == ref, pat
+    finally:
+        os.environ.pop("PAC_TILE_BLOCKS", None)
+        os.environ.pop("PAC_POISON_SMEM", None)
+
+
 def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
     """fp32 fast mode cannot be byte exact; it must report its quantiser-code mismatch rate (north_star)."""
     import pacb200_batch as pbat
