@@ -42,6 +42,23 @@ struct DBuf {
     template <typename U> U *as() { return reinterpret_cast<U *>(p); }
 };
 
+// pinned host buffer (small asynchronous read-backs that must not block the enqueueing thread)
+struct HBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename U> U *as() { return reinterpret_cast<U *>(p); }
+};
+
 template <typename T>
 struct TableSet {
     DevTables<T> dev;
@@ -62,7 +79,8 @@ struct PacCtx {
     cudaEvent_t evH[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
     DBuf w_pcm2, w_out2;
     cudaEvent_t evStart = nullptr;
-    std::vector<cudaEvent_t> evA, evB;
+    std::vector<cudaEvent_t> evA, evB, evG, evS[2];
+    HBuf hostState;
     cudaStream_t launchStream = nullptr;          // stream the launch helpers currently target (default: ctx->stream)
     std::string err;
     int64_t launches = 0;
@@ -558,6 +576,9 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     for (cudaEvent_t e : ctx->evA) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->evB) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->evG) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) for (cudaEvent_t e : ctx->evS[i]) cudaEventDestroy(e);
+    ctx->hostState.release();
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (auto &kv : ctx->tf) cudaFree(kv.second.mem);
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
@@ -633,7 +654,7 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM>, (1 << LOGM) / 4, smem));
     if (perSM < 1) perSM = 1;
     int64_t grid = (int64_t)ctx->numSMs * perSM;
-    if (ctx->launchStream) grid = a.nwork;       // overlapped tiles: short-lived CTAs let the scan/pack kernels of the previous tile in
+    if (ctx->launchStream) grid = a.nwork;       // overlapped tiles (a persistent grid here measured 460 vs 354 ms: it never yields SMs): short-lived CTAs let the scan/pack kernels of the previous tile in
     if (grid > a.nwork) grid = a.nwork;
     if (grid < 1) grid = 1;
     { KTimer kt(ctx, PAC_K_ANALYSIS); k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, LS(ctx)>>>(a); }
@@ -686,6 +707,13 @@ static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
 }
 
 // ------------------------------------------------------------------ encode (whole streams)
+// Schedule.  Streams are cut into groups (host buffers: about eight, so that copies pipeline; device buffers: one),
+// a group into time tiles of TB blocks.  Three internal CUDA streams:
+//   sA (low priority)   k_analysis of every tile, in order
+//   sB (high priority)  k_scan + k_pack of every tile, in order, one tile behind sA (double-buffered intermediates)
+//   sC                  H2D of the next group's PCM / D2H of the previous group's images (host buffers only)
+// The host enqueues group g+1 BEFORE it waits for group g's byte counts, so the device never drains between groups; only
+// the very last tile's scan+pack is not hidden under an analysis kernel.  The caller's stream is fenced on both sides.
 template <typename T>
 static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const int64_t *nSamples, int S, uint8_t *out,
                           int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace) {
@@ -698,14 +726,11 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         if (nb > maxBlocksAll) maxBlocksAll = nb;
     }
     if (cap < hdrB) FAIL(PAC_E_OVERFLOW, "cap smaller than the file header");
-    // streams are processed in groups so that staging + intermediates stay bounded
-    const int64_t workBudget = 1 << 18;                       // (stream, block) items resident at once
+    const int64_t workBudget = 1 << 18;                       // (stream, block) items per tile buffer
     int Sg = S;
     const int64_t stagingLimit = (int64_t)24 << 30;
     const bool staged = !pcmDev || !outDev;
     if (staged) {
-        // host buffers: groups are pipelined (H2D of group g+1 and D2H of group g-1 run on the copy stream while group g
-        // computes), so use about eight groups, each double-buffered within the staging limit
         int64_t per = (pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap);
         int64_t lim = stagingLimit / (2 * (per > 0 ? per : 1));
         if (lim < 1) lim = 1;
@@ -715,127 +740,178 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         if (Sg < 1) Sg = 1;
     }
     if (Sg > 8192) Sg = 8192;
-    int status = PAC_OK;
     const int nGroups = (S + Sg - 1) / Sg;
-    auto h2d_group = [&](int g) -> cudaError_t {            // stage group g's PCM on the copy stream
-        const int s0g = g * Sg, Scg = (S - s0g < Sg) ? S - s0g : Sg;
-        DBuf &buf = (g & 1) ? ctx->w_pcm2 : ctx->w_pcm;
-        cudaError_t e = buf.ensure((size_t)Sg * stride * 4 + 16);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(buf.p, pcm + (int64_t)s0g * stride * 2, (size_t)Scg * stride * 4, cudaMemcpyHostToDevice, ctx->sC);
-        if (e != cudaSuccess) return e;
-        return cudaEventRecord(ctx->evH[g & 1], ctx->sC);
-    };
-    if (staged) {
-        CK(cudaEventRecord(ctx->evStart, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->sC, ctx->evStart, 0));
-        if (!pcmDev) CK(h2d_group(0));
+    cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC;
+
+    // ---- per-stream inputs and state for ALL streams, uploaded once
+    CK(ctx->w_ns.ensure((size_t)S * 8));
+    CK(ctx->w_state.ensure((size_t)S * sizeof(StreamState)));
+    CK(ctx->w_hdr.ensure((size_t)S * hdrB));
+    CK(ctx->w_ovf.ensure((size_t)S * 4));
+    CK(ctx->hostState.ensure((size_t)S * (sizeof(StreamState) + 4)));         // pinned: results come back without blocking the host
+    StreamState *hSt = ctx->hostState.template as<StreamState>();
+    int *hOvf = reinterpret_cast<int *>(hSt + S);
+    {
+        std::vector<StreamState> st(S);
+        for (int s = 0; s < S; s++) { st[s].extraBits = 0; st[s].bitDeposit = 0; st[s].outOffset = hdrB; st[s].reserved = 0; }   // pacfile.py:269, Huffman.py:262
+        std::vector<uint8_t> hdr((size_t)S * hdrB);
+        for (int s = 0; s < S; s++) build_header(ctx, nSamples[s], hdr.data() + (size_t)s * hdrB);
+        CK(cudaMemcpyAsync(ctx->w_ns.p, nSamples, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->w_state.p, st.data(), (size_t)S * sizeof(StreamState), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->w_hdr.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)S * 4, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));               // the pageable vectors above go out of scope
     }
-    int grp = 0;
-    for (int s0 = 0; s0 < S; s0 += Sg, grp++) {
-        const int Sc = (S - s0 < Sg) ? S - s0 : Sg;
-        int64_t maxBlocks = 0;
-        for (int s = 0; s < Sc; s++) { int64_t nb = pac_num_blocks(ctx, nSamples[s0 + s]); if (nb > maxBlocks) maxBlocks = nb; }
-        int TB = (int)(workBudget / Sc);
+    CK(cudaEventRecord(ctx->evStart, ctx->stream));
+    CK(cudaStreamWaitEvent(sA, ctx->evStart, 0));
+    CK(cudaStreamWaitEvent(sB, ctx->evStart, 0));
+    CK(cudaStreamWaitEvent(sC, ctx->evStart, 0));
+
+    // ---- tile geometry per group, and the global tile numbering (buffer parity and events run across groups)
+    struct Group { int s0, Sc, TB, nTiles, tile0; int64_t maxBlocks; };
+    std::vector<Group> groups(nGroups);
+    int64_t nworkMax = 0;
+    int totalTiles = 0;
+    for (int g = 0; g < nGroups; g++) {
+        Group &G = groups[g];
+        G.s0 = g * Sg; G.Sc = (S - G.s0 < Sg) ? S - G.s0 : Sg;
+        G.maxBlocks = 0;
+        for (int s = 0; s < G.Sc; s++) { int64_t nb = pac_num_blocks(ctx, nSamples[G.s0 + s]); if (nb > G.maxBlocks) G.maxBlocks = nb; }
+        int TB = (int)(workBudget / G.Sc);
         {   // at least ~16 tiles: only the LAST tile's scan+pack is not hidden under the next tile's analysis
-            const int tbCap = (int)((maxBlocks + 15) / 16);
+            const int tbCap = (int)((G.maxBlocks + 15) / 16);
             if (TB > tbCap) TB = tbCap;
         }
         if (const char *tbe = getenv("PAC_TILE_BLOCKS")) TB = atoi(tbe);          // tests: force a tiling
         if (TB < 8) TB = 8;
-        if (TB > maxBlocks) TB = (int)maxBlocks;
-        if (trace) TB = (int)maxBlocks;                      // taps are copied out once per group
+        if (TB > G.maxBlocks) TB = (int)G.maxBlocks;
+        if (trace) TB = (int)G.maxBlocks;                    // taps are copied out once per group
+        G.TB = TB; G.nTiles = (int)((G.maxBlocks + TB - 1) / TB); G.tile0 = totalTiles;
+        totalTiles += G.nTiles;
+        if ((int64_t)G.Sc * TB > nworkMax) nworkMax = (int64_t)G.Sc * TB;
+    }
+    const int NBUF = totalTiles > 1 ? 2 : 1;
+    const size_t szLines = (size_t)nworkMax * 2 * M * sizeof(T), szBand = (size_t)nworkMax * 2 * kMaxBands * sizeof(T);
+    CK(ctx->w_lines.ensure(szLines * NBUF));
+    CK(ctx->w_smr.ensure(szBand * NBUF));
+    CK(ctx->w_bmax.ensure(szBand * NBUF));
+    CK(ctx->w_osc.ensure((size_t)nworkMax * 2 * NBUF));
+    CK(ctx->w_lrms.ensure((size_t)nworkMax * 4 * NBUF));
+    CK(ctx->w_ba.ensure((size_t)nworkMax * 2 * kMaxBands));
+    CK(ctx->w_sf.ensure((size_t)nworkMax * 2 * kMaxBands));
+    CK(ctx->w_tid.ensure((size_t)nworkMax * 2));
+    CK(ctx->w_nby.ensure((size_t)nworkMax * 2 * 4));
+    CK(ctx->w_coff.ensure((size_t)nworkMax * 2 * 8));
+    if (trace) { CK(ctx->w_trE.ensure((size_t)nworkMax * 8)); CK(ctx->w_trD.ensure((size_t)nworkMax * 8)); }
+    // NB: evA is created WITH timing on purpose.  Measured on B200 (512 x 60 s, device-resident): 354 ms per call, against
+    // 425 ms when evA carries cudaEventDisableTiming -- the cross-stream wait of sB on a timestamped record lets the
+    // high-priority scan kernel in promptly; with the light-weight event it trails the next analysis kernel.
+    static const int evaTiming = getenv("PAC_EVA_TIMING") ? atoi(getenv("PAC_EVA_TIMING")) : 1;
+    while ((int)ctx->evA.size() < totalTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, (evaTiming & 1) ? cudaEventDefault : cudaEventDisableTiming)); ctx->evA.push_back(e); }
+    while ((int)ctx->evB.size() < totalTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, (evaTiming & 2) ? cudaEventDefault : cudaEventDisableTiming)); ctx->evB.push_back(e); }
+    while ((int)ctx->evG.size() < nGroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evG.push_back(e); }
+    if (!pcmDev) { CK(ctx->w_pcm.ensure((size_t)Sg * stride * 4 + 16)); if (nGroups > 1) CK(ctx->w_pcm2.ensure((size_t)Sg * stride * 4 + 16)); }
+    if (!outDev) { CK(ctx->w_out.ensure((size_t)Sg * cap)); if (nGroups > 1) CK(ctx->w_out2.ensure((size_t)Sg * cap)); }
+
+    // PAC_TIMELINE=1: print when each group's copies and kernels ran (ms since the start of the call)
+    struct Mark { cudaEvent_t e; const char *what; int g; };
+    std::vector<Mark> marks;
+    const bool timeline = getenv("PAC_TIMELINE") != nullptr;
+    cudaEvent_t tl0 = nullptr;
+    auto mark = [&](cudaStream_t st, const char *what, int g) {
+        if (!timeline) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({e, what, g});
+    };
+    if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, ctx->stream); }
+
+    // H2D of a group's PCM goes in time slabs (one per tile, all streams of the group: a strided 2-D copy), each with its own
+    // event, so that the analysis of tile t starts as soon as samples < (t+1)*TB*M have landed -- the first kernel of the
+    // call waits for 1/nTiles of a group, not for a whole group.
+    auto h2d_group = [&](int g) -> cudaError_t {
+        const Group &G = groups[g];
+        DBuf &buf = (g & 1) ? ctx->w_pcm2 : ctx->w_pcm;
+        cudaError_t e = cudaSuccess;
+        if (g >= 2) e = cudaStreamWaitEvent(sC, ctx->evA[groups[g - 2].tile0 + groups[g - 2].nTiles - 1], 0);   // the buffer's previous reader is done
+        if (e != cudaSuccess) return e;
+        std::vector<cudaEvent_t> &evs = ctx->evS[g & 1];
+        while ((int)evs.size() < G.nTiles) { cudaEvent_t ev; e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; evs.push_back(ev); }
+        mark(sC, "h2d begin", g);
+        for (int t = 0; t < G.nTiles; t++) {
+            const int64_t a0 = (int64_t)t * G.TB * M;
+            int64_t a1 = (t == G.nTiles - 1) ? stride : (int64_t)(t + 1) * G.TB * M;
+            if (a1 > stride) a1 = stride;
+            if (a1 > a0) {
+                e = cudaMemcpy2DAsync(buf.template as<char>() + a0 * 4, (size_t)stride * 4, reinterpret_cast<const char *>(pcm + (int64_t)G.s0 * stride * 2) + a0 * 4,
+                                      (size_t)stride * 4, (size_t)(a1 - a0) * 4, (size_t)G.Sc, cudaMemcpyHostToDevice, sC);
+                if (e != cudaSuccess) return e;
+            }
+            e = cudaEventRecord(evs[t], sC);
+            if (e != cudaSuccess) return e;
+        }
+        mark(sC, "h2d end", g);
+        return cudaSuccess;
+    };
+
+    int status = PAC_OK;
+    auto enqueue_group = [&](int g) -> int {
+        const Group &G = groups[g];
+        const int Sc = G.Sc, s0 = G.s0, TB = G.TB;
         const int64_t nwork = (int64_t)Sc * TB;
-        // ---- inputs
         const int16_t *d_pcm;
         if (pcmDev) d_pcm = pcm + (int64_t)s0 * stride * 2;
         else {
-            d_pcm = ((grp & 1) ? ctx->w_pcm2 : ctx->w_pcm).as<int16_t>();
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->evH[grp & 1], 0));               // this group's PCM has landed
-            if (grp + 1 < nGroups) CK(h2d_group(grp + 1));                              // next group's copy overlaps this group's kernels
+            d_pcm = ((g & 1) ? ctx->w_pcm2 : ctx->w_pcm).template as<int16_t>();
+            if (g + 1 < nGroups) CK(h2d_group(g + 1));                                     // next group's copy overlaps this group's kernels
         }
         uint8_t *d_out;
         if (outDev) d_out = out + (int64_t)s0 * cap;
         else {
-            DBuf &ob = (grp & 1) ? ctx->w_out2 : ctx->w_out;
-            CK(ob.ensure((size_t)Sg * cap));
-            d_out = ob.as<uint8_t>();
-            if (grp >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->evD[grp & 1], 0));  // its previous contents have been copied out
+            d_out = ((g & 1) ? ctx->w_out2 : ctx->w_out).template as<uint8_t>();
+            if (g >= 2) CK(cudaStreamWaitEvent(sB, ctx->evD[g & 1], 0));                  // its previous contents have been copied out
         }
-        CK(ctx->w_ns.ensure((size_t)Sc * 8));
-        CK(cudaMemcpyAsync(ctx->w_ns.p, nSamples + s0, (size_t)Sc * 8, cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<StreamState> st(Sc);
-        for (int s = 0; s < Sc; s++) { st[s].extraBits = 0; st[s].bitDeposit = 0; st[s].outOffset = hdrB; st[s].reserved = 0; }   // pacfile.py:269, Huffman.py:262
-        CK(ctx->w_state.ensure((size_t)Sc * sizeof(StreamState)));
-        CK(cudaMemcpyAsync(ctx->w_state.p, st.data(), (size_t)Sc * sizeof(StreamState), cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<uint8_t> hdr((size_t)Sc * hdrB);
-        for (int s = 0; s < Sc; s++) build_header(ctx, nSamples[s0 + s], hdr.data() + (size_t)s * hdrB);
-        CK(ctx->w_hdr.ensure(hdr.size()));
-        CK(cudaMemcpyAsync(ctx->w_hdr.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CK(ctx->w_ovf.ensure((size_t)Sc * 4));
-        CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)Sc * 4, ctx->stream));
-        // ---- intermediates, double-buffered by tile parity so that scan+pack of tile i (stream sB, high priority) overlap the
-        //      analysis of tile i+1 (stream sA)
-        const int nTiles = (int)((maxBlocks + TB - 1) / TB);
-        const bool overlap = !trace && nTiles > 1;
-        const int NBUF = overlap ? 2 : 1;
-        const size_t szLines = (size_t)nwork * 2 * M * sizeof(T), szBand = (size_t)nwork * 2 * kMaxBands * sizeof(T);
-        CK(ctx->w_lines.ensure(szLines * NBUF));
-        CK(ctx->w_smr.ensure(szBand * NBUF));
-        CK(ctx->w_bmax.ensure(szBand * NBUF));
-        CK(ctx->w_osc.ensure((size_t)nwork * 2 * NBUF));
-        CK(ctx->w_lrms.ensure((size_t)nwork * 4 * NBUF));
-        CK(ctx->w_ba.ensure((size_t)nwork * 2 * kMaxBands));
-        CK(ctx->w_sf.ensure((size_t)nwork * 2 * kMaxBands));
-        CK(ctx->w_tid.ensure((size_t)nwork * 2));
-        CK(ctx->w_nby.ensure((size_t)nwork * 2 * 4));
-        CK(ctx->w_coff.ensure((size_t)nwork * 2 * 8));
-        if (trace) { CK(ctx->w_trE.ensure((size_t)nwork * 8)); CK(ctx->w_trD.ensure((size_t)nwork * 8)); }
-        if (overlap) {
-            while ((int)ctx->evA.size() < nTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evA.push_back(e); }
-            while ((int)ctx->evB.size() < nTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evB.push_back(e); }
-            CK(cudaEventRecord(ctx->evStart, ctx->stream));
-            CK(cudaStreamWaitEvent(ctx->sA, ctx->evStart, 0));
-            CK(cudaStreamWaitEvent(ctx->sB, ctx->evStart, 0));
-        }
-        int tile = 0;
-        for (int b0 = 0; b0 < maxBlocks; b0 += TB, tile++) {
-            const int nb = (maxBlocks - b0 < TB) ? (int)(maxBlocks - b0) : TB;
-            const int pbuf = overlap ? (tile & 1) : 0;
+        int t = 0;
+        for (int b0 = 0; b0 < G.maxBlocks; b0 += TB, t++) {
+            const int tile = G.tile0 + t;
+            const int nb = (G.maxBlocks - b0 < TB) ? (int)(G.maxBlocks - b0) : TB;
+            const int pbuf = NBUF == 2 ? (tile & 1) : 0;
             AnalysisArgs<T> aa{};
-            aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.as<int64_t>(); aa.blocks = nullptr;
+            aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.template as<int64_t>() + s0; aa.blocks = nullptr;
             aa.S = Sc; aa.b0 = b0; aa.nb = nb; aa.nwork = (int64_t)Sc * nb;
-            aa.lines = reinterpret_cast<T *>(ctx->w_lines.as<char>() + szLines * pbuf);
-            aa.smr = reinterpret_cast<T *>(ctx->w_smr.as<char>() + szBand * pbuf);
-            aa.bmax = reinterpret_cast<T *>(ctx->w_bmax.as<char>() + szBand * pbuf);
-            aa.oscale = ctx->w_osc.as<uint8_t>() + (size_t)nwork * 2 * pbuf;
-            aa.lrms = ctx->w_lrms.as<uint32_t>() + (size_t)nwork * pbuf;
+            aa.lines = reinterpret_cast<T *>(ctx->w_lines.template as<char>() + szLines * pbuf);
+            aa.smr = reinterpret_cast<T *>(ctx->w_smr.template as<char>() + szBand * pbuf);
+            aa.bmax = reinterpret_cast<T *>(ctx->w_bmax.template as<char>() + szBand * pbuf);
+            aa.oscale = ctx->w_osc.template as<uint8_t>() + (size_t)nworkMax * 2 * pbuf;
+            aa.lrms = ctx->w_lrms.template as<uint32_t>() + (size_t)nworkMax * pbuf;
             aa.dbg_mdct = nullptr; aa.dbg_bthr = nullptr;
-            if (overlap) {
-                if (tile >= 2) CK(cudaStreamWaitEvent(ctx->sA, ctx->evB[tile - 2], 0));      // buffer reuse
-                ctx->launchStream = ctx->sA;
-            }
+            if (tile >= 2) CK(cudaStreamWaitEvent(sA, ctx->evB[tile - 2], 0));            // tile buffer reuse
+            if (!pcmDev) CK(cudaStreamWaitEvent(sA, ctx->evS[g & 1][t], 0));              // this tile's samples have landed
+            if (t == 0) mark(sA, "analysis begin", g);
+            ctx->launchStream = sA;
             int rc = launch_analysis<T>(ctx, aa);
-            if (overlap) { CK(cudaEventRecord(ctx->evA[tile], ctx->sA)); CK(cudaStreamWaitEvent(ctx->sB, ctx->evA[tile], 0)); ctx->launchStream = ctx->sB; }
             if (rc) { ctx->launchStream = nullptr; return rc; }
+            CK(cudaEventRecord(ctx->evA[tile], sA));
+            if (t == G.nTiles - 1) mark(sA, "analysis end", g);
+            CK(cudaStreamWaitEvent(sB, ctx->evA[tile], 0));
+            ctx->launchStream = sB;
             ScanArgs<T> sa{};
-            sa.S = Sc; sa.b0 = b0; sa.nb = nb; sa.nSamples = ctx->w_ns.as<int64_t>(); sa.state = ctx->w_state.as<StreamState>();
+            sa.S = Sc; sa.b0 = b0; sa.nb = nb; sa.nSamples = aa.nSamples; sa.state = ctx->w_state.template as<StreamState>() + s0;
             sa.lines = aa.lines; sa.smr = aa.smr; sa.bmax = aa.bmax; sa.lrms = aa.lrms;
-            sa.ba = ctx->w_ba.as<uint8_t>(); sa.sf = ctx->w_sf.as<uint8_t>(); sa.tableID = ctx->w_tid.as<uint8_t>();
-            sa.nbytes = ctx->w_nby.as<uint32_t>(); sa.chunkOff = ctx->w_coff.as<long long>();
-            sa.trExtra = trace ? ctx->w_trE.as<long long>() : nullptr; sa.trDeposit = trace ? ctx->w_trD.as<long long>() : nullptr;
+            sa.ba = ctx->w_ba.template as<uint8_t>(); sa.sf = ctx->w_sf.template as<uint8_t>(); sa.tableID = ctx->w_tid.template as<uint8_t>();
+            sa.nbytes = ctx->w_nby.template as<uint32_t>(); sa.chunkOff = ctx->w_coff.template as<long long>();
+            sa.trExtra = trace ? ctx->w_trE.template as<long long>() : nullptr; sa.trDeposit = trace ? ctx->w_trD.template as<long long>() : nullptr;
             if ((rc = launch_scan<T>(ctx, sa))) { ctx->launchStream = nullptr; return rc; }
             PackArgs<T> pa{};
-            pa.S = Sc; pa.b0 = b0; pa.nb = nb; pa.nSamples = ctx->w_ns.as<int64_t>();
+            pa.S = Sc; pa.b0 = b0; pa.nb = nb; pa.nSamples = aa.nSamples;
             pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
             pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = d_out; pa.cap = cap; pa.perChunk = 0;
-            pa.overflow = ctx->w_ovf.as<int>(); pa.o_mant = nullptr;
-            pa.header = ctx->w_hdr.as<uint8_t>(); pa.headerBytes = hdrB;
+            pa.overflow = ctx->w_ovf.template as<int>() + s0; pa.o_mant = nullptr;
+            pa.header = ctx->w_hdr.template as<uint8_t>() + (size_t)s0 * hdrB; pa.headerBytes = hdrB;
             rc = launch_pack<T>(ctx, pa);
-            if (overlap) { CK(cudaEventRecord(ctx->evB[tile], ctx->sB)); ctx->launchStream = nullptr; }
+            ctx->launchStream = nullptr;
             if (rc) return rc;
+            CK(cudaEventRecord(ctx->evB[tile], sB));
             if (trace) {      // single tile (TB == maxBlocks): copy the taps of this stream group
-                CK(cudaStreamSynchronize(ctx->stream));
+                CK(cudaStreamSynchronize(sB));
                 const int64_t B = maxBlocksAll;
                 std::vector<T> hl, hs;
                 std::vector<uint8_t> hba((size_t)nwork * 2 * kMaxBands), hsf((size_t)nwork * 2 * kMaxBands), htid((size_t)nwork * 2), hosc((size_t)nwork * 2);
@@ -854,46 +930,68 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
                 for (int s = 0; s < Sc; s++) {
                     int64_t nbs = pac_num_blocks(ctx, nSamples[s0 + s]);
                     for (int64_t b = 0; b < nbs; b++) {
-                        int64_t w = (int64_t)s * nb + b, g = (int64_t)(s0 + s) * B + b;
-                        if (trace->lrms) trace->lrms[g] = (int32_t)hlr[w];
-                        if (trace->extraBits) trace->extraBits[g] = hE[w];
-                        if (trace->bitDeposit) trace->bitDeposit[g] = hD[w];
+                        int64_t w = (int64_t)s * nb + b, gi = (int64_t)(s0 + s) * B + b;
+                        if (trace->lrms) trace->lrms[gi] = (int32_t)hlr[w];
+                        if (trace->extraBits) trace->extraBits[gi] = hE[w];
+                        if (trace->bitDeposit) trace->bitDeposit[gi] = hD[w];
                         for (int ch = 0; ch < 2; ch++) {
-                            if (trace->oscale) trace->oscale[g * 2 + ch] = hosc[w * 2 + ch];
-                            if (trace->tableID) trace->tableID[g * 2 + ch] = htid[w * 2 + ch];
-                            if (trace->nbytes) trace->nbytes[g * 2 + ch] = (int32_t)hnby[w * 2 + ch];
+                            if (trace->oscale) trace->oscale[gi * 2 + ch] = hosc[w * 2 + ch];
+                            if (trace->tableID) trace->tableID[gi * 2 + ch] = htid[w * 2 + ch];
+                            if (trace->nbytes) trace->nbytes[gi * 2 + ch] = (int32_t)hnby[w * 2 + ch];
                             for (int bd = 0; bd < NB; bd++) {
-                                if (trace->ba) trace->ba[(g * 2 + ch) * NB + bd] = hba[(w * 2 + ch) * kMaxBands + bd];
-                                if (trace->sf) trace->sf[(g * 2 + ch) * NB + bd] = hsf[(w * 2 + ch) * kMaxBands + bd];
-                                if (trace->smr) trace->smr[(g * 2 + ch) * NB + bd] = (double)hs[(w * 2 + ch) * kMaxBands + bd];
+                                if (trace->ba) trace->ba[(gi * 2 + ch) * NB + bd] = hba[(w * 2 + ch) * kMaxBands + bd];
+                                if (trace->sf) trace->sf[(gi * 2 + ch) * NB + bd] = hsf[(w * 2 + ch) * kMaxBands + bd];
+                                if (trace->smr) trace->smr[(gi * 2 + ch) * NB + bd] = (double)hs[(w * 2 + ch) * kMaxBands + bd];
                             }
                             if (trace->lines)
-                                for (int i = 0; i < M; i++) trace->lines[(g * 2 + ch) * M + i] = (double)hl[(w * 2 + ch) * M + i];
+                                for (int i = 0; i < M; i++) trace->lines[(gi * 2 + ch) * M + i] = (double)hl[(w * 2 + ch) * M + i];
                         }
                     }
                 }
             }
         }
-        if (overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->evB[nTiles - 1], 0));
-        // ---- results of this group
-        CK(cudaMemcpyAsync(st.data(), ctx->w_state.p, (size_t)Sc * sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
-        std::vector<int> ovf(Sc);
-        CK(cudaMemcpyAsync(ovf.data(), ctx->w_ovf.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        // this group's final per-stream state -> pinned host memory, behind its last pack
+        CK(cudaMemcpyAsync(hSt + s0, ctx->w_state.template as<StreamState>() + s0, (size_t)Sc * sizeof(StreamState), cudaMemcpyDeviceToHost, sB));
+        CK(cudaMemcpyAsync(hOvf + s0, ctx->w_ovf.template as<int>() + s0, (size_t)Sc * 4, cudaMemcpyDeviceToHost, sB));
+        CK(cudaEventRecord(ctx->evG[g], sB));
+        mark(sB, "pack end", g);
+        return PAC_OK;
+    };
+    auto collect_group = [&](int g) -> int {
+        const Group &G = groups[g];
+        CK(cudaEventSynchronize(ctx->evG[g]));
         int64_t maxBytes = 0;
-        for (int s = 0; s < Sc; s++) {
-            outBytes[s0 + s] = st[s].outOffset;
-            if (finalState) { finalState[(s0 + s) * 2] = st[s].bitDeposit; finalState[(s0 + s) * 2 + 1] = st[s].extraBits; }
-            if (ovf[s] || st[s].outOffset > cap) { status = PAC_E_OVERFLOW; outBytes[s0 + s] = -st[s].outOffset; }
-            else if (st[s].outOffset > maxBytes) maxBytes = st[s].outOffset;
+        for (int s = G.s0; s < G.s0 + G.Sc; s++) {
+            outBytes[s] = hSt[s].outOffset;
+            if (finalState) { finalState[s * 2] = hSt[s].bitDeposit; finalState[s * 2 + 1] = hSt[s].extraBits; }
+            if (hOvf[s] || hSt[s].outOffset > cap) { status = PAC_E_OVERFLOW; outBytes[s] = -hSt[s].outOffset; }
+            else if (hSt[s].outOffset > maxBytes) maxBytes = hSt[s].outOffset;
         }
-        if (!outDev) {                                    // the kernels of this group are complete (stream synchronised above)
+        if (!outDev) {                                    // the kernels of this group are complete (event synchronised above)
+            const uint8_t *d_out = ((g & 1) ? ctx->w_out2 : ctx->w_out).template as<uint8_t>();
+            mark(sC, "d2h begin", g);
             if (maxBytes > 0)
-                CK(cudaMemcpy2DAsync(out + (int64_t)s0 * cap, (size_t)cap, d_out, (size_t)cap, (size_t)maxBytes, (size_t)Sc, cudaMemcpyDeviceToHost, ctx->sC));
-            CK(cudaEventRecord(ctx->evD[grp & 1], ctx->sC));
+                CK(cudaMemcpy2DAsync(out + (int64_t)G.s0 * cap, (size_t)cap, d_out, (size_t)cap, (size_t)maxBytes, (size_t)G.Sc, cudaMemcpyDeviceToHost, sC));
+            mark(sC, "d2h end", g);
+            CK(cudaEventRecord(ctx->evD[g & 1], sC));
         }
+        return PAC_OK;
+    };
+
+    if (!pcmDev) CK(h2d_group(0));
+    int rc = PAC_OK;
+    for (int g = 0; g < nGroups && rc == PAC_OK; g++) {
+        rc = enqueue_group(g);
+        if (rc == PAC_OK && g >= 1) rc = collect_group(g - 1);
     }
-    if (staged) CK(cudaStreamSynchronize(ctx->sC));
+    if (rc == PAC_OK) rc = collect_group(nGroups - 1);
+    // fence: the caller's stream continues after everything issued here (also on the error path, so buffers can be reused)
+    cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC);
+    if (timeline) {
+        for (const Mark &m : marks) { float ms = 0; cudaEventElapsedTime(&ms, tl0, m.e); fprintf(stderr, "[pac timeline] group %d %-15s %9.2f ms\n", m.g, m.what, ms); cudaEventDestroy(m.e); }
+        cudaEventDestroy(tl0);
+    }
+    if (rc != PAC_OK) return rc;
     if (status == PAC_E_OVERFLOW) ctx->err = "output capacity too small for at least one stream (outBytes[s] = -needed)";
     return status;
 }
