@@ -685,8 +685,13 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         if (rc) return rc;
         a.band_of_line = tb.band_of_line;
     }
-    constexpr int WARPS = 4;
-    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, LS(ctx)>>>(a); }
+    static const int warps = getenv("PAC_SCAN_WARPS") ? atoi(getenv("PAC_SCAN_WARPS")) : 4;      // experiment
+    {
+        KTimer kt(ctx, PAC_K_SCAN);
+        if (warps == 1) k_scan<T, 1><<<a.S, 32, 0, LS(ctx)>>>(a);
+        else if (warps == 2) k_scan<T, 2><<<(a.S + 1) / 2, 64, 0, LS(ctx)>>>(a);
+        else k_scan<T, 4><<<(a.S + 3) / 4, 128, 0, LS(ctx)>>>(a);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
