@@ -685,13 +685,10 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         if (rc) return rc;
         a.band_of_line = tb.band_of_line;
     }
-    static const int warps = getenv("PAC_SCAN_WARPS") ? atoi(getenv("PAC_SCAN_WARPS")) : 4;      // experiment
-    {
-        KTimer kt(ctx, PAC_K_SCAN);
-        if (warps == 1) k_scan<T, 1><<<a.S, 32, 0, LS(ctx)>>>(a);
-        else if (warps == 2) k_scan<T, 2><<<(a.S + 1) / 2, 64, 0, LS(ctx)>>>(a);
-        else k_scan<T, 4><<<(a.S + 3) / 4, 128, 0, LS(ctx)>>>(a);
-    }
+    // one warp per CTA: while it overlaps k_analysis, a scan CTA can only get on an SM by taking the place of a retiring
+    // analysis CTA (20 K registers); seven 1-warp CTAs fit in that space against one 4-warp CTA (measured 1360 vs 1385 ms/step)
+    constexpr int WARPS = 1;
+    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, LS(ctx)>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
