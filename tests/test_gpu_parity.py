@@ -269,6 +269,64 @@ def test_full_corpus_fp64_byte_exact(e64, manifest):
     assert len(names) >= 2
 
 
+def test_full_corpus_fp32_within_tolerance_of_oracle(e32, oracle):
+    """fp32 fast mode on EVERY block of every inputs/*.wav (not only the 16 dumped ones), against the oracle's per-block
+    taps, with the tolerance formulas of test_analysis_fp32_within_1e5_of_reference:
+      * every MDCT line of every block (whose M/S decision agrees) within tolerance -- no exceptions;
+      * SMR: within tolerance except where findpeaks (psychoac.py:158-191) flips.  Its strict comparisons
+        P[k] > P[k-1], P[k] > P[k+1] between two nearly equal neighbouring bins are decided by rounding noise (1e-16 in the
+        reference, 1e-7 in fp32); a flip moves or removes ONE masker and shifts one threshold curve by up to a few dB over
+        ~1 Bark.  That is a discrete mismatch like a flipped M/S decision, not an accuracy loss, so it is counted and
+        bounded (<= 0.1 % of SMR values, <= 2 % of blocks) rather than required to be zero;
+      * decision / allocation mismatch rates and the size difference are printed and bounded."""
+    import pacb200_batch as pbat
+    files = corpus_files()
+    names = sorted(files)
+    pcms = [pbat.read_wav(files[n])[1] for n in names]
+    L = max(len(p) for p in pcms)
+    batch = np.zeros((len(names), L, 2), np.int16)
+    ns = np.array([len(p) for p in pcms], np.int64)
+    for i, p in enumerate(pcms):
+        batch[i, :len(p)] = p
+    outs, tr = e32.encode_batch(batch, nSamples=ns, trace=True)
+    worst_l = 0.0
+    nblk = nlr = nosc = nsmr = nsmr_bad = nblk_bad = 0
+    es_all = []
+    mism = {"ba": 0, "sf": 0, "tableID": 0}
+    cnt = {"ba": 0, "sf": 0, "tableID": 0}
+    bytes_gpu = bytes_ref = 0
+    for i, n in enumerate(names):
+        enc, otr, _ = oracle.encode_stream(pcms[i], trace=True)
+        nb = len(otr["lrms"])
+        bytes_gpu += len(outs[i]); bytes_ref += len(enc)
+        same = (tr["lrms"][i][:nb] == otr["lrms"]) & np.all(tr["oscale"][i][:nb] == otr["oscale"], axis=1)
+        nblk += nb; nlr += int(np.sum(tr["lrms"][i][:nb] != otr["lrms"])); nosc += int(np.sum(np.any(tr["oscale"][i][:nb] != otr["oscale"], axis=1)))
+        ref = otr["lines"][same]
+        got = tr["lines"][i][:nb][same]
+        mx = np.max(np.abs(ref), axis=(1, 2), keepdims=True)
+        el = np.abs(got - ref) / (1e-5 * np.abs(ref) + 1e-7 * np.maximum(mx, 1e-300))
+        rs = otr["smr"][same]
+        es = np.abs(tr["smr"][i][:nb][same] - rs) / (1e-5 * np.maximum(np.abs(rs), 10.0))
+        if el.size:
+            worst_l = max(worst_l, float(el.max()))
+            nsmr += es.size; nsmr_bad += int(np.sum(es > 1.0)); nblk_bad += int(np.sum(np.any(es > 1.0, axis=(1, 2))))
+            es_all.append(es.ravel())
+        for f in mism:
+            mism[f] += int(np.sum(tr[f][i][:nb] != otr[f])); cnt[f] += otr[f].size
+    es_all = np.concatenate(es_all)
+    print("fp32 vs oracle over %d files / %d blocks: worst line error %.3f x tol; SMR error median %.3f x tol, 99.9 %% quantile "
+          "%.3f x tol, over tolerance %d of %d values (%.4f %%) in %d blocks (peak-picking flips, worst %.2f dB); "
+          "M/S decision mismatches %d, overall-scale mismatches %d; mismatch rates %s; coded bytes %d vs %d (%+.4f %%)"
+          % (len(names), nblk, worst_l, float(np.median(es_all)), float(np.quantile(es_all, 0.999)), nsmr_bad, nsmr,
+             100.0 * nsmr_bad / nsmr, nblk_bad, float(es_all.max()) * 1e-4, nlr, nosc,
+             {f: "%.4f %%" % (100.0 * mism[f] / cnt[f]) for f in mism}, bytes_gpu, bytes_ref, 100.0 * (bytes_gpu / bytes_ref - 1)))
+    assert worst_l <= 1.0
+    assert nsmr_bad <= 1e-3 * nsmr and nblk_bad <= 0.02 * nblk and float(np.quantile(es_all, 0.999)) <= 1.0
+    assert nlr <= 0.001 * nblk and nosc <= 0.001 * nblk
+    assert all(mism[f] <= 0.01 * cnt[f] for f in mism)
+    assert abs(bytes_gpu / bytes_ref - 1) < 0.002
+
+
 def test_edge_streams_fp64_vs_oracle(e64, oracle):
     cases = [("empty", np.zeros((0, 2), np.int16)), ("one", synth_pcm(1, 1)), ("1023", synth_pcm(2, 1023)),
              ("1024", synth_pcm(3, 1024)), ("1025", synth_pcm(4, 1025)), ("ragged", synth_pcm(5, 7001)),
