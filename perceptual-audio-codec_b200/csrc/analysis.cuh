@@ -62,8 +62,10 @@ struct AnalysisSmem {
     static constexpr int N = 2 * M;
     static constexpr int NT = M / 4;
     using T2 = typename Vec2<T>::type;
-    T2 XF[2][M + 2];       // time samples x[ch][n] (viewed as T[2][N+4]); later F1[ch][0..M]
-    T2 W[2][M + 2];        // FFT work; later F2_M, F2_S; finally the four per-line SMR candidate arrays
+    // fp32 mode runs its 1024-point FFTs in the padded layout of fft.cuh (one spare element per 16): rows of M + M/16
+    static constexpr int ROW = FASTK ? M + M / 16 : M + 2;
+    T2 XF[2][ROW];         // time samples x[ch][n] (viewed as T[2][2*ROW], padded in fp32 mode); later F1[ch][0..M]
+    T2 W[2][ROW];          // FFT work; later F2_M, F2_S; finally the four per-line SMR candidate arrays
     T Lb[2][M];            // scaled MDCT lines L, R
     T P[M + 8];            // |spectrum|^2 of the current curve
     static constexpr int MLM = FASTK ? 1 : M / 2;                // the direct evaluation's masker list (fp64 / mono kernels)
@@ -410,13 +412,17 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables<T> &tb = a.tab;
     const int NB = a.bands.nBands;
-    T *xt = reinterpret_cast<T *>(&sm.XF[0][0]);      // x[ch][n] at xt[ch*(N+4) + n]
-    constexpr int XS = N + 4;
+    constexpr bool FAST = sizeof(T) == 4;
+    constexpr int ROW = S::ROW;
+    T *xt = reinterpret_cast<T *>(&sm.XF[0][0]);      // x[ch][n] at xt[ch*XS + XI(n)]
+    constexpr int XS = 2 * ROW;
+    // fp32: sample pair m = (x[2m], x[2m+1]) is complex element m of the in-place raw FFT, stored at its padded position
+    auto XI = [](int n) { return FAST ? n + 2 * (n >> 5) : n; };
+    auto PI = [](int m) { return fft_pad<FAST>(m); };
 
     // per-thread constants for its 4 lines i = tid + NT*j
     // line ownership: fp64 (direct evaluation) thread t owns lines t + NT*j; fp32 (scan-based evaluation): warp w owns the
     // 64-line half-chunks w and 2*NW-1-w, two adjacent lines per lane in each (see masked_curve_fast step 4).
-    constexpr bool FAST = sizeof(T) == 4;
     const int lineBase[2] = {64 * warp + 2 * lane, 64 * (2 * NW - 1 - warp) + 2 * lane};
     auto LI = [&](int j) { return FAST ? lineBase[j >> 1] + (j & 1) : tid + NT * j; };
     T zl[4], zlo[4], tiq[4], mld[4];
@@ -458,7 +464,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                     int code = c < 0 ? -c : c;
                     if (code & 32768) code -= 32768;          // -32768 dequantises to 0 (quantize.py:133-138)
                     T f = (T)(2 * code) / (T)65535;           // quantize.py:141
-                    xt[ch * XS + n] = c < 0 ? -f : f;
+                    xt[ch * XS + XI(n)] = c < 0 ? -f : f;
                 }
             }
         } else {
@@ -467,7 +473,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             for (int j = 0; j < 2 * N / NT; j++) {
                 int e = tid + NT * j;
                 int ch = e / N, n = e - ch * N;
-                xt[ch * XS + n] = (T)src[e];
+                xt[ch * XS + XI(n)] = (T)src[e];
             }
         }
         __syncthreads();
@@ -492,7 +498,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                     sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
                 }
                 __syncthreads();
-                fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 2);
+                fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, ROW, tb.tw, 2);
                 for (int e = tid; e < 2 * H; e += NT) {
                     int ch = e / H, k = e - ch * H;
                     T2 y = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
@@ -514,7 +520,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 const DevTables<double> &tdd = a.tabd;
                 auto xd = [&](int ch, int n) -> double {
                     double v;
-                    if (a.pcm) v = (double)__float2int_rn(xt[ch * XS + n] * 32767.5f) * (2.0 / 65535.0);
+                    if (a.pcm) v = (double)__float2int_rn(xt[ch * XS + XI(n)] * 32767.5f) * (2.0 / 65535.0);
                     else v = a.blocks[w * 2 * N + ch * N + n];
                     return v * tdd.sinw[n];
                 };
@@ -560,26 +566,26 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         // ------------------------------------------------ B. raw FFTs -> LRMS decision (codec.py:96-102)
         // fp64: raw FFTs of L, R in W.  fp32: the raw FFTs run IN PLACE in XF and, in the same batch of four, the FFTs of the
         // sine*Hann windowed channels in W (the fp32 MDCT has already consumed x).
-        T2(*RAW)[M + 2] = FAST ? sm.XF : sm.W;
+        T2(*RAW)[ROW] = FAST ? sm.XF : sm.W;
         for (int e = tid; e < 2 * M; e += NT) {
             int ch = e / M, m = e - ch * M;
-            const T2 x2 = sm.XF[ch][m];                   // (x[2m], x[2m+1])
+            const T2 x2 = sm.XF[ch][PI(m)];               // (x[2m], x[2m+1])
             if constexpr (FAST) {
                 const T2 s2 = reinterpret_cast<const T2 *>(tb.sinw)[m], h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
-                sm.W[ch][m] = mk2<T>((x2.x * s2.x) * h2.x, (x2.y * s2.y) * h2.y);      // window.py:37 then psychoac.py:428
+                sm.W[ch][PI(m)] = mk2<T>((x2.x * s2.x) * h2.x, (x2.y * s2.y) * h2.y);      // window.py:37 then psychoac.py:428
             } else {
                 sm.W[ch][m] = x2;
             }
         }
         if (tid == 0) sm.lrms = 0;
         __syncthreads();
-        if constexpr (FAST) fft_dif<T, LOGM, NT>(&sm.XF[0][0], 4, M + 2, tb.tw, 1);
-        else fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+        if constexpr (FAST) fft_dif<T, LOGM, NT, true>(&sm.XF[0][0], 4, ROW, tb.tw, 1);
+        else fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, ROW, tb.tw, 1);
         for (int bd = warp; bd < NB; bd += NW) {
             T dr = 0, di = 0, sr = 0, si = 0;
             for (int k = a.bands.lo[bd] + lane; k < a.bands.lo[bd + 1]; k += 32) {
-                T2 l = rfft_split<T, LOGM>(RAW[0], k, tb.tw_split);
-                T2 r = rfft_split<T, LOGM>(RAW[1], k, tb.tw_split);
+                T2 l = rfft_split<T, LOGM, FAST>(RAW[0], k, tb.tw_split);
+                T2 r = rfft_split<T, LOGM, FAST>(RAW[1], k, tb.tw_split);
                 T l2r = l.x * l.x - l.y * l.y, l2i = l.x * l.y + l.y * l.x;
                 T r2r = r.x * r.x - r.y * r.y, r2i = r.x * r.y + r.y * r.x;
                 dr += l2r - r2r; di += l2i - r2i;
@@ -599,7 +605,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         if constexpr (FAST) {
             for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M, into XF (the raw spectra are dead)
                 int ch = e / (M + 1), k = e - ch * (M + 1);
-                sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
+                sm.XF[ch][k] = rfft_split<T, LOGM, true>(sm.W[ch], k, tb.tw_split);
             }
             __syncthreads();
         }
@@ -613,7 +619,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 sm.W[ch][m] = mk2<T>(x2.x * h2.x, x2.y * h2.y);
             }
             __syncthreads();
-            fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, M + 2, tb.tw, 1);
+            fft_dif<T, LOGM, NT>(&sm.W[0][0], 2, ROW, tb.tw, 1);
             for (int e = tid; e < 2 * (M + 1); e += NT) {         // F1[ch][k], k = 0..M
                 int ch = e / (M + 1), k = e - ch * (M + 1);
                 sm.XF[ch][k] = rfft_split<T, LOGM>(sm.W[ch], k, tb.tw_split);
