@@ -49,8 +49,8 @@ struct FastSmem {
     double Sp[M + 2];             // exclusive prefix sums (in double) of the plateau intensities A_k over the bins
     double wtot[16];
     float V[M], Wq[M];            // dense per bin: down-scan injection, up-scan injection (quiet maskers)
-    float4 loud[M / 2];           // maskers louder than 40 dB: (c0 - up/2, up, zk_hi, zk_lo)
-    short loudEU[M / 2];          // their first upper-skirt line
+    float4 loud[M / 2];           // maskers louder than 40 dB: (B_hi, up, B_lo, first upper-skirt line as int bits) with
+                                  // B = c0 - up/2 - up * z_masker formed in double: exponent at line i = up * z_i + B
     unsigned short loudPrefix[M + 2];   // number of loud maskers with bin < k
     float totD[16], totA[16];
 };
@@ -214,9 +214,9 @@ __device__ __forceinline__ float spl_any(float i) { return spl_fast(i); }
 __device__ __forceinline__ double spl_any(double i) { return spl_of<double>(i); }
 
 template <int LOGM>
-__device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, const float2 *F, int tap, float drop,
+__device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, const float2 *F, int tap, float drop,
                                                  const DevTables<float> *tbp, const FastTables *ftp, const double *zpeakd,
-                                                 const double *zlined, int lb0, int lb1) {
+                                                 const double *zlined, int lb0, int lb1, uint32_t kU0, uint32_t kU1) {
     constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
     const DevTables<float> &tb = *tbp;
     const FastTables &ft = *ftp;
@@ -297,8 +297,9 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
     for (int q = 0; q < 4; q++) {
         fs.loudPrefix[k0 + q] = (unsigned short)offs;
         if (loudf & (1u << q)) {
-            fs.loud[offs] = make_float4(c0s[q] - 0.5f * ups[q], ups[q], btq[q].z, btq[q].w);
-            fs.loudEU[offs] = (short)(beuq[q] >> 16);
+            const double Bd = ((double)c0s[q] - 0.5 * (double)ups[q]) - (double)ups[q] * ((double)btq[q].z + (double)btq[q].w);
+            const float Bh = (float)Bd;
+            fs.loud[offs] = make_float4(Bh, ups[q], (float)(Bd - (double)Bh), __int_as_float((int)(beuq[q] >> 16)));
             offs++;
         }
     }
@@ -375,22 +376,25 @@ __device__ __noinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true>
         const float2 a2v = *reinterpret_cast<const float2 *>(&sm.P[l0]);
         float x0 = a2v.x, x1 = a2v.y;
         const float4 zz = *reinterpret_cast<const float4 *>(&ft.lineZ[l0]);      // l0 is even: (z0_hi, z0_lo, z1_hi, z1_lo)
-        const float z0 = zz.x, z0l = zz.y, z1 = zz.z, z1l = zz.w;
-        const int hfirst = l0 & ~63;
-        const int mfull = fs.loudPrefix[ft.kcountU[hfirst]];        // upper skirt starts at or before the half-chunk
-        const int mhi = fs.loudPrefix[ft.kcountU[hfirst + 63]];     // ... at or before its last line
+        const float z0 = zz.x, z0l = zz.y;
+        const float dz01 = (zz.z - zz.x) + (zz.w - zz.y);          // Bark gap to the lane's second line
+        const uint32_t kU = hh ? kU1 : kU0;
+        const int mfull = fs.loudPrefix[kU & 0xffffu];        // upper skirt starts at or before the half-chunk
+        const int mhi = fs.loudPrefix[kU >> 16];              // ... at or before its last line
         int m = 0;
         for (; m < mfull; m++) {
             const float4 p = fs.loud[m];
-            const float d0 = (z0 - p.z) + (z0l - p.w), d1 = (z1 - p.z) + (z1l - p.w);
-            x0 += ex2_approx(fmaf(p.y, d0, p.x));
-            x1 += ex2_approx(fmaf(p.y, d1, p.x));
+            const float e0 = fmaf(p.y, z0, p.x) + fmaf(p.y, z0l, p.z);
+            const float e1 = fmaf(p.y, dz01, e0);
+            x0 += ex2_approx(e0);
+            x1 += ex2_approx(e1);
         }
         for (; m < mhi; m++) {
             const float4 p = fs.loud[m];
-            const int eu = fs.loudEU[m];
-            const float d0 = (z0 - p.z) + (z0l - p.w), d1 = (z1 - p.z) + (z1l - p.w);
-            const float t0 = ex2_approx(fmaf(p.y, d0, p.x)), t1 = ex2_approx(fmaf(p.y, d1, p.x));
+            const int eu = __float_as_int(p.w);
+            const float e0 = fmaf(p.y, z0, p.x) + fmaf(p.y, z0l, p.z);
+            const float e1 = fmaf(p.y, dz01, e0);
+            const float t0 = ex2_approx(e0), t1 = ex2_approx(e1);
             x0 += (l0 >= eu) ? t0 : 0.f;
             x1 += (l0 + 1 >= eu) ? t1 : 0.f;
         }
@@ -435,6 +439,13 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
     }
 
+    // fp32: bins whose upper skirt starts at or before the first / last line of this warp's two half-chunks (static)
+    uint32_t kU0 = 0, kU1 = 0;
+    if constexpr (FAST) {
+        const int h0 = lineBase[0] & ~63, h1 = lineBase[1] & ~63;
+        kU0 = (uint32_t)a.ft.kcountU[h0] | (uint32_t)a.ft.kcountU[h0 + 63] << 16;
+        kU1 = (uint32_t)a.ft.kcountU[h1] | (uint32_t)a.ft.kcountU[h1 + 63] << 16;
+    }
     if (tid < 8) sm.P[M + tid] = 0;
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         const int s = (int)(w / a.nb);
@@ -653,7 +664,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
 #pragma unroll 1
             for (int c = 0; c < 6; c++) {
                 const float4 r = masked_curve_fast<LOGM>(sm, srcs[c], c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, a.tabd.zpeak, a.tabd.zline,
-                                                         lineBase[0], lineBase[1]);
+                                                         lineBase[0], lineBase[1], kU0, kU1);
                 thr[c][0] = r.x; thr[c][1] = r.y; thr[c][2] = r.z; thr[c][3] = r.w;
             }
         } else {
