@@ -189,7 +189,10 @@ def main():
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
-    ap.add_argument("--ref-seconds", type=float, default=4.0)
+    ap.add_argument("--ref-seconds", type=float, default=16.0, help="seconds per stream of the bounded CPU sample (one stream per host thread)")
+    ap.add_argument("--tbps", type=float, default=2.27, help="targetBitsPerSample (pacfile.py:455 default 2.27)")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json configs[4]: also run the bitrate sweep 64..256 kb/s/ch (encode and decode-only, extra 'bitrate_sweep' key)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--decode", action="store_true", help="also time decode-only throughput of the coded corpus (extra 'decode' key)")
@@ -214,7 +217,7 @@ def main():
     dev = torch.device("cuda", local)
     S, n = args.streams, int(args.seconds * FS)
     mine = list(range(rank, S, world))                   # stream s -> rank s mod world
-    eng = _pacb200.Engine(local, args.precision)
+    eng = _pacb200.Engine(local, args.precision, targetBitsPerSample=args.tbps)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)      # torch's CUDA events now bracket the library's work
     nblk = eng.num_blocks(n)
     t0 = time.time()
@@ -299,6 +302,48 @@ def main():
                "kernels_ms": {k: v[0] for k, v in tmd.items() if v[1]}}
         del pcm_out
 
+    # ---- bitrate sweep (BASELINE.json configs[4]): encode and decode-only per target rate
+    sweep = None
+    if args.sweep:
+        sweep = []
+        Sd = min(len(mine), 1024)
+        pcm_out = torch.empty(Sd, nblk * 1024 + 1024, 2, dtype=torch.int16, device=dev)
+        beg_of = lambda c: np.arange(Sd, dtype=np.int64) * c
+
+        def timed(fn):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record()
+            r = fn()
+            a1.record()
+            barrier()
+            t = torch.tensor([a0.elapsed_time(a1) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return r, float(t.item())
+
+        for kbps in (64, 96, 128, 192, 256):
+            tb = kbps * 1000.0 / FS
+            e2 = _pacb200.Engine(local, args.precision, targetBitsPerSample=tb)
+            e2.set_stream(torch.cuda.current_stream().cuda_stream)
+            cap2 = e2.encode_bound(n)
+            out2 = torch.empty(len(mine), cap2, dtype=torch.uint8, device=dev)
+            e2.encode_batch(pcm, out=out2, cap=cap2)                              # warm
+            (_, ob2), t_enc = timed(lambda: e2.encode_batch(pcm, out=out2, cap=cap2))
+            ob_h = np.asarray(ob2, dtype=np.int64)[:Sd]
+            e2.decode_batch_strided(out2, beg_of(cap2), ob_h, pcm_out, pcm_out.shape[1])   # warm
+            _, t_dec = timed(lambda: e2.decode_batch_strided(out2, beg_of(cap2), ob_h, pcm_out, pcm_out.shape[1]))
+            tot = torch.tensor([float(np.sum(ob2)), float(Sd)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tot)
+            sweep.append({"kbps_per_channel": kbps, "targetBitsPerSample": round(tb, 4),
+                          "encode_audio_s_per_s": audio_s / t_enc, "decode_audio_s_per_s": float(tot[1].item()) * args.seconds / t_dec,
+                          "decode_streams": int(tot[1].item()), "coded_bytes": int(tot[0].item()),
+                          "coded_kbps_per_channel": float(tot[0].item()) * 8 / 1000.0 / (audio_s * 2)})
+            e2.close()
+            del out2
+        del pcm_out
+
     # ---- e2e through the C ABI with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -337,6 +382,14 @@ def main():
             "traffic_source": traffic.get("source") if traffic else None,
             "algorithmic_bytes_per_block": algo, "blocks_per_launch": blocks_local / max(a_cnt, 1),
             "avg_launch_ms": a_ms / max(a_cnt, 1), "launches": a_cnt,
+            # the stage is issue-bound, so the same launch is also placed on the SM issue roofline: warp instructions per block
+            # (ncu smsp__inst_executed, profiles/) over the launch time against 4 schedulers x SMs x SM clock
+            "issue": ({"warp_inst_per_block": traffic["warp_inst_per_block"],
+                       "achieved_ginst_s": traffic["warp_inst_per_block"] * blocks_local / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0,
+                       "peak_ginst_s": 4 * torch.cuda.get_device_properties(dev).multi_processor_count * (clk.get("sm_max_mhz") or 1965.0) * 1e-3,
+                       "frac": traffic["warp_inst_per_block"] * blocks_local / (a_ms * 1e-3) / 1e9
+                               / (4 * torch.cuda.get_device_properties(dev).multi_processor_count * (clk.get("sm_max_mhz") or 1965.0) * 1e-3) if a_ms > 0 else 0.0}
+                      if traffic and traffic.get("warp_inst_per_block") and args.precision == "fp32" else None),
             "note": "SMR is transcendental-bound, not HBM-bound (SURVEY.md App. E); kernel time split: "
                     + ", ".join("%s %.1f ms" % (k, v[0]) for k, v in tm.items() if v[1])}
 
@@ -356,12 +409,14 @@ def main():
                 "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
                 "config": {"workload": "synthetic corpus %d x %.0f s 44.1 kHz stereo int16 (tones+noise+transients), %s mode, streams sharded s mod N"
                                        % (S, args.seconds, args.precision),
-                           "streams": S, "seconds_per_stream": args.seconds, "blocks_per_stream": nblk, "targetBitsPerSample": 2.27,
+                           "streams": S, "seconds_per_stream": args.seconds, "blocks_per_stream": nblk, "targetBitsPerSample": args.tbps,
                            "cache": "inputs (%.1f GB per rank) far larger than the 126 MB L2; no flush needed" % (len(mine) * n * 4 / 1e9),
                            "coded_bytes": total_bytes},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         if dec:
             line["decode"] = dec
+        if sweep:
+            line["bitrate_sweep"] = sweep
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

@@ -448,7 +448,8 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     }
     if (tid < 8) sm.P[M + tid] = 0;
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
-        const int s = (int)(w / a.nb);
+        // 32-bit division when the tile allows it (a 64-bit division is a ~100-instruction subroutine, paid by every CTA)
+        const int s = a.nwork <= 0xffffffffll ? (int)((uint32_t)w / (uint32_t)a.nb) : (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
         if (a.poisonOn) {             // results must not depend on what a previous block left in shared memory
             __syncthreads();

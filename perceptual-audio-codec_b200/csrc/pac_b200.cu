@@ -650,6 +650,8 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     static bool configured[2] = {false, false};
     (void)configured;
     CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char *cv = getenv("PAC_CARVEOUT_KB"))                                // L1-size experiments
+        CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv) * 100 / 228));
     int perSM = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM>, (1 << LOGM) / 4, smem));
     if (perSM < 1) perSM = 1;

@@ -57,7 +57,7 @@ k_pack(const PackArgs<T> a) {
     for (int64_t c = (int64_t)blockIdx.x * kPackWarps + warp; c < nchunks; c += (int64_t)gridDim.x * kPackWarps) {
         const int64_t w = c >> 1;
         const int ch = (int)(c & 1);
-        const int s = (int)(w / a.nb);
+        const int s = nchunks <= 0xffffffffll ? (int)((uint32_t)w / (uint32_t)a.nb) : (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
         if (a.nSamples) {
             long long nblk = (a.nSamples[s] + M - 1) / M + 1;

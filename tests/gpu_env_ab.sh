@@ -1,0 +1,15 @@
+#!/bin/bash
+# gpu_env_ab.sh -- short bench under different experiment environment settings (diagnostic)
+S=${S:-592}; SEC=${SEC:-10}
+mkdir -p gpurun_out
+run() {
+  env "$@" python bench.py --streams $S --seconds $SEC --steps 3 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('%-40s step %.2f ms  analysis %.1f ns/block  %s' % ('$*', d['ms_per_step'], 1e6*r['avg_launch_ms']/r['blocks_per_launch'], r['note'].split(';')[-1]))
+" | tee -a gpurun_out/env_ab.log
+}
+run X=0
+run PAC_EXTRA_SMEM=30000
+run PAC_CARVEOUT_KB=164
+run PAC_CARVEOUT_KB=196
