@@ -342,7 +342,9 @@ def main():
                           "coded_kbps_per_channel": float(tot[0].item()) * 8 / 1000.0 / (audio_s * 2)})
             e2.close()
             del out2
+            torch.cuda.empty_cache()                      # cudaMalloc'd library workspaces of the next engine need the room
         del pcm_out
+        torch.cuda.empty_cache()
 
     # ---- e2e through the C ABI with pinned host buffers
     e2e = None
@@ -352,6 +354,7 @@ def main():
         out_h = torch.empty(len(mine), cap, dtype=torch.uint8, pin_memory=True)
         del out
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()                          # the staging buffers are the library's own cudaMalloc
         ph, oh = pcm_h.numpy(), out_h.numpy()
         eng.encode_batch(ph, out=oh, cap=cap)             # warm (allocates the staging buffers)
         barrier()

@@ -190,6 +190,12 @@ int pac_huffman_select(PacCtx *ctx, const uint32_t *mag, const int32_t *ba, int 
 int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *extraBits, int maxMantBits,
                  const double *smr /*[n][nBands]*/, const int32_t *lrms /*[n] masks*/, int32_t *bits /*[n][nBands]*/,
                  int64_t *bitDifference /*[n]*/);
+/* The allocators HEAD's codec does not call, kept for API parity: mode 0 bitalloc.BitAllocUniform (bitalloc.py:22-57, level may be
+ * NULL), 1 BitAllocConstSNR (:60-91, level[n][nBands] = peakSPL replicated per band), 2 BitAllocConstMNR (:94-125, level = SMR), on n
+ * independent problems.  Returns PAC_E_ARG where the reference's `while remaining_bits > 0` would never terminate (bits left, no band
+ * able to take one). */
+int pac_bitalloc_alt(PacCtx *ctx, int mode, int n, const double *bitBudget, int maxMantBits, const double *level /*[n][nBands]*/,
+                     int32_t *bits /*[n][nBands]*/);
 /* quantize.py: ScaleFactor :148-177 (n scalars), vQuantizeUniform :91-117, vDequantizeUniform :120-145,
  * vMantissa :315-342, vDequantize :345-376 */
 int pac_scale_factor(PacCtx *ctx, const double *x, int n, int nScaleBits, int nMantBits, int32_t *scale);

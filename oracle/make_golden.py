@@ -352,6 +352,32 @@ def make_kats():
                              "nLines": [int(v) for v in nLines], "SMR": np.asarray(smr).tolist(),
                              "bits": [int(b) for b in bits], "bitDifference": int(diff)})
         k["bitalloc"] = ba_cases
+        # the allocators HEAD does not call (bitalloc.py:22-125), on the same SMR vector and on the band peak SPLs
+        alt = []
+        B = R.bitalloc
+        peak = float(np.max(smr) + 20.0)
+        for budget in (1000, 2116.48, 300.0, 6000.0, 25.0, 523 * 3):
+            alt.append({"mode": "uniform", "bitBudget": budget, "nLines": [int(v) for v in nLines],
+                        "bits": [int(b) for b in B.BitAllocUniform(budget, 16, 25, nLines)]})
+        # BitAllocConstSNR / ConstMNR only terminate when the greedy loop lands on exactly zero remaining bits (otherwise
+        # `while remaining_bits > 0` spins for ever, bitalloc.py:74,109).  The C restatement detects that state, so it is used
+        # here to PICK budgets for which the reference returns; the recorded answers are the reference's own.
+        import oracle as orc
+        O = orc.get()
+        for mode, fn, level in (("constmnr", B.BitAllocConstMNR, np.asarray(smr, dtype=float)), ("constsnr", B.BitAllocConstSNR, peak)):
+            ok = []
+            for budget in list(range(40, 4000, 37)) + [512 * 16, 512 * 20]:
+                try:
+                    O.bitalloc_alt(mode, budget, 16, 25, nLines, level)
+                    ok.append(budget)
+                except RuntimeError:
+                    pass
+            assert len(ok) >= 4, (mode, ok)
+            for budget in [ok[i] for i in sorted(set(np.linspace(0, len(ok) - 1, 8).astype(int).tolist()))]:
+                got = fn(budget, 16, 25, nLines, level.copy() if hasattr(level, "copy") else level)
+                alt.append({"mode": mode, "bitBudget": budget, "nLines": [int(v) for v in nLines],
+                            "level": np.broadcast_to(np.asarray(level, dtype=float), (25,)).tolist(), "bits": [int(b) for b in got]})
+        k["bitalloc_alt"] = alt
         # Huffman tables: structure facts (Huffman.py:138-153, huffmanTables.pickle)
         h = R.new_huffman()
         k["huffman_tables"] = {str(i): {"nsym": len(t.encodingTable), "maxkey": max(t.encodingTable),

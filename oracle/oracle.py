@@ -173,6 +173,8 @@ class Oracle:
         L.orc_vmantissa.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.orc_vdequantize.argtypes = [C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, dp]
         L.orc_bitalloc.argtypes = [C.c_double, C.c_int64, C.c_int, C.c_int, ip, dp, ip, ip, C.POINTER(C.c_int64)]
+        L.orc_bitalloc_alt.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, ip, dp, ip]
+        L.orc_bitalloc_alt.restype = C.c_int
         L.orc_calc_bthr.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_calc_smrs.argtypes = [dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, ip, C.c_int, dp, dp]
         L.orc_stereo_smr.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, ip, C.c_int, ip, C.c_int, ip, dp, dp, dp]
@@ -237,6 +239,15 @@ class Oracle:
         self.lib.orc_bitalloc(bitBudget, int(extraBits), maxMantBits, nBands, _ptr(nLines, C.c_int32),
                               _ptr(SMR, C.c_double), _ptr(LRMS, C.c_int32), _ptr(bits, C.c_int32), C.byref(d))
         return bits, int(d.value)
+
+    def bitalloc_alt(self, mode, bitBudget, maxMantBits, nBands, nLines, level=None):
+        """bitalloc.py:22-125; mode 'uniform' | 'constsnr' | 'constmnr'.  Raises where the reference would not terminate."""
+        m = {"uniform": 0, "constsnr": 1, "constmnr": 2}[mode]
+        nLines = np.array(nLines, dtype=np.int32); bits = np.zeros(nBands, dtype=np.int32)
+        lv = np.zeros(nBands) if level is None else np.ascontiguousarray(np.broadcast_to(np.asarray(level, dtype=np.float64), (nBands,)))
+        if self.lib.orc_bitalloc_alt(m, float(bitBudget), maxMantBits, nBands, _ptr(nLines, C.c_int32), _ptr(lv, C.c_double), _ptr(bits, C.c_int32)):
+            raise RuntimeError("the reference allocator does not terminate for this input")
+        return bits
 
     def calc_smrs(self, data, mdct, scale, sampleRate, nLines):
         data = np.array(data, dtype=np.float64); mdct = np.array(mdct, dtype=np.float64)

@@ -338,6 +338,53 @@ int orc_bitalloc(double bitBudget, int64_t extraBits, int maxMantBits, int nBand
     return 0;
 }
 
+/* The allocators HEAD does not call (bitalloc.py:22-125), restated for the widened API surface.
+ * mode 0: BitAllocUniform (:22-57, `level` unused); 1: BitAllocConstSNR (:60-91, level[b] = peakSPL for every b);
+ * 2: BitAllocConstMNR (:94-125, level = SMR).  The two water-filling loops of the reference do not terminate when bits
+ * remain but no band can take another one (every band is full or wider than what is left); that state is detected and
+ * reported as -1 (the reference would spin for ever). */
+int orc_bitalloc_alt(int mode, double bitBudget, int maxMantBits, int nBands, const int32_t *nLines, const double *level,
+                     int32_t *bits)
+{
+    if (mode == 0) {
+        int64_t total = 0;
+        for (int b = 0; b < nBands; b++) total += nLines[b];
+        int per = (int)(bitBudget / (double)total);                 /* int() truncation, :32 */
+        double used = 0;
+        for (int b = 0; b < nBands; b++) { bits[b] = per; used += (double)per * nLines[b]; }
+        double remaining = bitBudget - used;                        /* :37 */
+        if (remaining != 0.0) {
+            int64_t line = 0;
+            while (remaining > 0) {
+                int b = (int)(line % nBands);
+                if (nLines[b] == 0 && total == 0) return -1;
+                remaining -= nLines[b];
+                if (remaining < 0) break;
+                if (bits[b] < maxMantBits) bits[b] += 1;
+                line++;
+            }
+        }
+    } else {
+        double floor_[ORC_MAX_BANDS];
+        double remaining = bitBudget;
+        for (int b = 0; b < nBands; b++) { bits[b] = 0; floor_[b] = level[b]; }
+        while (remaining > 0) {
+            int can = 0;
+            for (int b = 0; b < nBands; b++) if (bits[b] < maxMantBits && remaining - nLines[b] >= 0) can = 1;
+            if (!can) return -1;
+            int iMax = 0;
+            for (int b = 1; b < nBands; b++) if (floor_[b] > floor_[iMax]) iMax = b;   /* argmax: first index wins */
+            if (bits[iMax] < maxMantBits && remaining - nLines[iMax] >= 0) { bits[iMax] += 1; remaining -= nLines[iMax]; }
+            floor_[iMax] -= 6.0;
+        }
+    }
+    for (int b = 0; b < nBands; b++) {
+        if (bits[b] < 2) bits[b] = 0;                               /* mid-tread: no 1-bit mantissas */
+        if (bits[b] > maxMantBits) bits[b] = maxMantBits;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ masking thresholds */
 
 typedef struct {

@@ -81,6 +81,11 @@ void orc_vdequantize(int scale, const int64_t *m, int n, int nScaleBits, int nMa
 int  orc_bitalloc(double bitBudget, int64_t extraBits, int maxMantBits, int nBands, const int32_t *nLines,
                   const double *SMR, const int32_t *LRMS, int32_t *bits, int64_t *bitDifference); /* bitalloc.py:129-184 */
 
+/* bitalloc.py:22-125: mode 0 BitAllocUniform, 1 BitAllocConstSNR (level = peakSPL per band), 2 BitAllocConstMNR (level = SMR);
+ * returns -1 where the reference's loop would never terminate */
+int  orc_bitalloc_alt(int mode, double bitBudget, int maxMantBits, int nBands, const int32_t *nLines, const double *level,
+                      int32_t *bits);
+
 /* masked threshold of one (already sine-windowed) time block; applies the Hann window IN PLACE
  * exactly as the reference does.  psychoac.py:409-456 */
 void orc_calc_bthr(double *data, int N, int nMDCTLines, int sampleRate, int noDrop, double *thr);

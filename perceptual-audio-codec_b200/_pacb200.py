@@ -96,6 +96,7 @@ def lib():
     L.pac_masked_threshold.argtypes = [vp, dp, C.c_int, C.c_int, dp]
     L.pac_huffman_select.argtypes = [vp, C.POINTER(C.c_uint32), i32p, C.c_int, i32p, i64p]
     L.pac_bitalloc.argtypes = [vp, C.c_int, dp, i64p, C.c_int, dp, i32p, i32p, i64p]
+    L.pac_bitalloc_alt.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int, dp, i32p]
     L.pac_scale_factor.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, i32p]
     L.pac_vquantize_uniform.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.pac_vdequantize_uniform.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int, C.c_int, dp]
@@ -415,6 +416,19 @@ class Engine(object):
         self._ck(lib().pac_bitalloc(self.ctx, n, _p(bb, C.c_double), _p(eb, C.c_int64), int(maxMantBits), _p(smr, C.c_double),
                                     _p(lm, C.c_int32), _p(bits, C.c_int32), _p(diff, C.c_int64)))
         return bits, diff
+
+    def bitalloc_alt(self, mode, bitBudget, maxMantBits, level=None):
+        """bitalloc.py:22-125 on n problems; mode 'uniform' | 'constsnr' | 'constmnr'; level [n][nBands] (peak SPL / SMR)"""
+        m = {"uniform": 0, "constsnr": 1, "constmnr": 2}[mode]
+        bb = np.ascontiguousarray(np.atleast_1d(np.asarray(bitBudget, np.float64)))
+        n = bb.shape[0]
+        lv = None
+        if m:
+            lv = np.ascontiguousarray(np.broadcast_to(np.asarray(level, np.float64).reshape(-1, self.nBands), (n, self.nBands)))
+        bits = np.zeros((n, self.nBands), np.int32)
+        self._ck(lib().pac_bitalloc_alt(self.ctx, m, n, _p(bb, C.c_double), int(maxMantBits), _p(lv, C.c_double) if m else None,
+                                        _p(bits, C.c_int32)))
+        return bits
 
     def scale_factor(self, x, nScaleBits, nMantBits):
         x = np.ascontiguousarray(np.atleast_1d(x), np.float64)

@@ -1631,6 +1631,29 @@ extern "C" int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const i
     return PAC_OK;
 }
 
+extern "C" int pac_bitalloc_alt(PacCtx *ctx, int mode, int n, const double *bitBudget, int maxMantBits, const double *level,
+                                int32_t *bits) {
+    if (!ctx) return PAC_E_ARG;
+    if (n <= 0 || !bitBudget || !bits || mode < 0 || mode > 2 || (mode > 0 && !level)) FAIL(PAC_E_ARG, "bad arguments to pac_bitalloc_alt");
+    CK(cudaSetDevice(ctx->device));
+    const int NB = ctx->bands.nBands;
+    CK(ctx->w_misc.ensure((size_t)n * 8)); CK(ctx->w_misc3.ensure((size_t)n * NB * 8));
+    CK(ctx->w_misc4.ensure((size_t)n * 4)); CK(ctx->w_misc5.ensure((size_t)n * NB * 4));
+    CK(cudaMemcpyAsync(ctx->w_misc.p, bitBudget, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (mode > 0) CK(cudaMemcpyAsync(ctx->w_misc3.p, level, (size_t)n * NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_bitalloc_alt<<<(n + 3) / 4, 128, 0, ctx->stream>>>(n, mode, ctx->w_misc.as<double>(), maxMantBits, ctx->w_misc3.as<double>(),
+                                                         ctx->w_misc5.as<int32_t>(), ctx->w_misc4.as<int32_t>(), ctx->bands);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<int32_t> st((size_t)n);
+    CK(cudaMemcpyAsync(bits, ctx->w_misc5.p, (size_t)n * NB * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(st.data(), ctx->w_misc4.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++)
+        if (st[i]) FAIL(PAC_E_ARG, "pac_bitalloc_alt: bits remain but no band can take one -- the reference loop (bitalloc.py:74,109) never terminates for this input");
+    return PAC_OK;
+}
+
 // small helper for the element-wise quantiser entry points
 #define ELEMWISE(IN_T, OUT_T, inptr, outptr, n, launch)                                                        \
     do {                                                                                                      \

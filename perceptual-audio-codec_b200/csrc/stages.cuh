@@ -90,6 +90,63 @@ __global__ void k_bitalloc(int n, const double *bitBudget, const long long *extr
     if (lane == 0) diff[p] = d;
 }
 
+// The allocators HEAD does not call (bitalloc.py:22-125), one warp per problem, lane b owns band b.
+// mode 0 BitAllocUniform (:22-57), 1 BitAllocConstSNR (:60-91, level = peakSPL per band), 2 BitAllocConstMNR (:94-125, level = SMR).
+// status[p] = 1 where the reference's `while remaining_bits > 0` would never end (bits left but no band can take one).
+__global__ void k_bitalloc_alt(int n, int mode, const double *bitBudget, int maxMantBits, const double *level, int32_t *bits,
+                               int32_t *status, BandInfo bands) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const int NB = bands.nBands;
+    const bool inband = lane < NB;
+    const int nl = inband ? bands.lo[lane + 1] - bands.lo[lane] : 0;
+    const double budget = bitBudget[p];
+    int b = 0, st = 0;
+    if (mode == 0) {
+        const int total = bands.lo[NB];
+        const int per = (int)(budget / (double)total);                       // :32
+        // sum(allocation * nLines) is an exact integer sum; the subtraction from bitBudget is the one rounding (:37)
+        double remaining = budget - (double)((long long)per * total);
+        b = per;
+        if (remaining != 0.0) {
+            // the walk over bands is sequential but tiny: every lane replays it and keeps its own band's count
+            long long line = 0;
+            if (total == 0) st = 1;
+            while (!st && remaining > 0) {
+                const int bd = (int)(line % NB);
+                remaining -= (double)(bands.lo[bd + 1] - bands.lo[bd]);
+                if (remaining < 0) break;
+                if (bd == lane && b < maxMantBits) b += 1;
+                line++;
+            }
+        }
+    } else {
+        double fl = inband ? level[(int64_t)p * NB + lane] : 0.0;
+        double remaining = budget;
+        while (remaining > 0) {
+            const bool can = inband && b < maxMantBits && remaining - (double)nl >= 0;
+            if (__ballot_sync(0xffffffffu, can) == 0u) { st = 1; break; }
+            // argmax of the noise floors, first index wins (np.argmax)
+            const unsigned long long key = inband ? sortable(fl) : 0ull;
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, inband ? hi : 0u);
+            const bool c1 = inband && hi == mh;
+            const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+            const int iMax = __ffs(__ballot_sync(0xffffffffu, c1 && lo == ml)) - 1;
+            const int nlm = bands.lo[iMax + 1] - bands.lo[iMax];
+            const int bm = __shfl_sync(0xffffffffu, b, iMax);
+            const bool take = bm < maxMantBits && remaining - (double)nlm >= 0;
+            if (take) remaining -= (double)nlm;
+            if (lane == iMax) { if (take) b += 1; fl -= 6.0; }
+        }
+    }
+    if (b < 2) b = 0;                                                          // mid-tread: no 1-bit mantissas
+    if (b > maxMantBits) b = maxMantBits;
+    if (inband) bits[(int64_t)p * NB + lane] = b;
+    if (lane == 0) status[p] = st;
+}
+
 // Huffman.encodeData (Huffman.py:274-309) on caller-supplied unsigned mantissas: total code length under each of
 // the 10 tables (escape = escape code + bitAlloc raw bits), strictly-shortest wins, ties keep the lowest ID.
 __global__ void k_huff_select(const uint32_t *mag, const int32_t *ba, int n, const unsigned long long *lenLut, EncConsts ec,

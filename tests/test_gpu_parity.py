@@ -146,6 +146,48 @@ def test_shim_bitalloc(kats, oracle, pb):
         assert list(b1[0]) == list(b2) and int(d1[0]) == d2, i
 
 
+def test_shim_bitalloc_alt(kats, oracle, pb):
+    """bitalloc.py:22-125 through pac_bitalloc_alt: the reference's own answers, random problems vs the oracle, and the
+    inputs for which the reference never returns."""
+    import bitalloc
+    pb.engine(sampleRate=48000, nMDCTLines=512)              # the layout of the six-tone KAT
+    fns = {"uniform": bitalloc.BitAllocUniform, "constsnr": bitalloc.BitAllocConstSNR, "constmnr": bitalloc.BitAllocConstMNR}
+    for c in kats["bitalloc_alt"]:
+        nl = np.array(c["nLines"])
+        if c["mode"] == "uniform":
+            got = fns["uniform"](c["bitBudget"], 16, 25, nl)
+        elif c["mode"] == "constsnr":
+            got = fns["constsnr"](c["bitBudget"], 16, 25, nl, c["level"][0])
+        else:
+            got = fns["constmnr"](c["bitBudget"], 16, 25, nl, np.array(c["level"]))
+        assert list(got) == c["bits"], (c["mode"], c["bitBudget"])
+    e = pb.engine()
+    rng = np.random.default_rng(5)
+    nchk = 0
+    for i in range(300):
+        budget = float(rng.integers(1, 9000)) if i % 3 else float(rng.uniform(1, 9000))
+        lv = rng.uniform(-30, 90, 25)
+        if i % 7 == 0:
+            lv[:] = lv[0]                                      # ties: first index must win
+        assert list(e.bitalloc_alt("uniform", budget, 16)[0]) == list(oracle.bitalloc_alt("uniform", budget, 16, 25, NL44))
+        for mode in ("constsnr", "constmnr"):
+            try:
+                want = oracle.bitalloc_alt(mode, budget, 16, 25, NL44, lv)
+            except RuntimeError:
+                with pytest.raises(pb.PacError):
+                    e.bitalloc_alt(mode, budget, 16, lv)
+                continue
+            assert list(e.bitalloc_alt(mode, budget, 16, lv)[0]) == list(want), (mode, budget)
+            nchk += 1
+    assert nchk > 20
+    # a batch in one launch
+    budgets = np.array([c["bitBudget"] for c in kats["bitalloc_alt"] if c["mode"] == "uniform"], dtype=np.float64)
+    pb.engine(sampleRate=48000, nMDCTLines=512)
+    e2 = pb.engine(sampleRate=48000, nMDCTLines=512)
+    got = e2.bitalloc_alt("uniform", budgets, 16)
+    assert [list(r) for r in got] == [c["bits"] for c in kats["bitalloc_alt"] if c["mode"] == "uniform"]
+
+
 def test_shim_calcsmrs_sixtone(kats):
     """psychoac.py:696-713 through the mono kernel (N = 1024, fs = 48000)."""
     import mdct

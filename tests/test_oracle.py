@@ -109,6 +109,16 @@ def test_bitalloc_kats(oracle, kats):
         assert diff == c["bitDifference"]
 
 
+def test_bitalloc_alt_kats(oracle, kats):
+    """bitalloc.py:22-125 (BitAllocUniform / ConstSNR / ConstMNR): the reference's own answers, and the non-terminating state."""
+    for c in kats["bitalloc_alt"]:
+        bits = oracle.bitalloc_alt(c["mode"], c["bitBudget"], 16, 25, c["nLines"], c.get("level"))
+        assert list(bits) == c["bits"], (c["mode"], c["bitBudget"])
+    c = kats["bitalloc_alt"][-1]
+    with pytest.raises(RuntimeError):                       # 0.48 bits can never be placed: the reference spins for ever
+        oracle.bitalloc_alt("constmnr", 2116.48, 16, 25, c["nLines"], c["level"])
+
+
 def test_huffman_table_facts(oracle, kats):
     for tid, f in kats["huffman_tables"].items():
         t = oracle.tables[int(tid)]
