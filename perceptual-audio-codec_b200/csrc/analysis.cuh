@@ -197,7 +197,8 @@ __device__ __forceinline__ void masked_curve(SMEM &sm, const DevTables<T> &tb, S
 // sums over bins (4-level block sums), and only the upper skirts of maskers louder than 40 dB pairwise -- over the
 // lines above them only.  tests/model_analysis.py:curve_v2 is the numpy statement of exactly this procedure.
 // Scans: thread t owns lines 4t..4t+3; pairwise part: warp w owns half-chunks w and 2NW-1-w (2 lines per lane each).
-// Deliberately NOT inlined: it is called six times per block and the kernel must stay inside the instruction cache.
+// Force-inlined into the single `#pragma unroll 1` loop over the six curves: as a real call its table pointers (kernel
+// parameters) were reached through generic loads.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
