@@ -196,6 +196,12 @@ int pac_bitalloc(PacCtx *ctx, int n, const double *bitBudget, const int64_t *ext
  * able to take one). */
 int pac_bitalloc_alt(PacCtx *ctx, int mode, int n, const double *bitBudget, int maxMantBits, const double *level /*[n][nBands]*/,
                      int32_t *bits /*[n][nBands]*/);
+/* Histogram.generateStatistics (Huffman.py:71-83), the data-parallel half of HuffmanTrainer.countFreq (:184-185): occurrences of every
+ * unsigned mantissa code < nbins among codes[0..n) (host or device pointer) and the position base+i of each code's first occurrence
+ * (-1 where absent; the reference's dict keeps first-insertion order, which breaks frequency ties in makeHuffmanNodeQueue :93-108).
+ * Codes >= nbins are ignored.  The tree itself (:221-246) is a few hundred nodes of host work and stays in the Python shim. */
+int pac_histogram(PacCtx *ctx, const uint32_t *codes, int64_t n, int64_t base, int nbins, int64_t *counts /*[nbins]*/,
+                  int64_t *first /*[nbins]*/);
 /* quantize.py: ScaleFactor :148-177 (n scalars), vQuantizeUniform :91-117, vDequantizeUniform :120-145,
  * vMantissa :315-342, vDequantize :345-376 */
 int pac_scale_factor(PacCtx *ctx, const double *x, int n, int nScaleBits, int nMantBits, int32_t *scale);

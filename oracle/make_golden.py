@@ -392,6 +392,40 @@ def make_kats():
             w = h.withdrawBits()
             seq.append([dep, int(w), int(h.bitDeposit)])
         k["withdraw"] = seq
+        # Huffman trainer (Huffman.py:156-250) on seeded geometric codes, two countFreq calls, then a second trainer in the same
+        # process (the class-level statistics dict keeps counting, :30-34)
+        def trainer_codes(seed, n, p):
+            g = np.random.default_rng(seed)
+            c = g.geometric(p, n) - 1
+            c[g.integers(0, n, n // 50)] = g.integers(0, 30000, n // 50)       # rare large codes -> escapes
+            return c
+        H = R.Huffman
+        cwd = os.getcwd()
+        os.chdir(R.dir)
+        try:
+            c1 = trainer_codes(20161018, 40000, 0.03)
+            t1 = H.HuffmanTrainer(11)
+            t1.countFreq([int(v) for v in c1[:25000]])
+            t1.countFreq([int(v) for v in c1[25000:]])
+            t1.constructHuffmanTable()
+            tab1 = dict(t1.huffmanCodeTable)
+            c2 = trainer_codes(7, 20000, 0.2)
+            t2 = H.HuffmanTrainer(12)
+            t2.countFreq([int(v) for v in c2])
+            t2.constructHuffmanTable()
+            tab2 = dict(t2.huffmanCodeTable)
+            with open("huffmanTables.pickle", "rb") as fh:
+                import pickle
+                stored = pickle.load(fh)
+            assert stored[11].encodingTable == tab1 and stored[12].encodingTable == tab2 and len(stored) == 12
+        finally:
+            os.chdir(cwd)
+        k["huffman_trainer"] = {"gen": "rng=default_rng(seed); c=geometric(p,n)-1; c[rng.integers(0,n,n//50)]=rng.integers(0,30000,n//50)",
+                                "first": {"seed": 20161018, "n": 40000, "p": 0.03, "split": 25000,
+                                          "table": {str(a): b for a, b in tab1.items()}},
+                                "second": {"seed": 7, "n": 20000, "p": 0.2, "table": {str(a): b for a, b in tab2.items()}}}
+        # (getMatchScore, Huffman.py:50-62, is Python-2-only as written -- np.array(dict.values()) -- and HEAD never calls it, so it
+        # is not exercised here; with the class-level probability dict it compares the dict with itself and returns 3.0.)
     with open(os.path.join(GOLD, "kats.json"), "w") as f:
         json.dump(k, f, indent=0)
     print("kats written")

@@ -356,3 +356,43 @@ def get():
     if _singleton is None:
         _singleton = Oracle()
     return _singleton
+
+
+# ---------------------------------------------------------------- Huffman trainer (Huffman.py:27-250), test infrastructure
+def train_huffman(chunks, low_freq=10, escape_code=-1, state=None):
+    """CPU restatement of HuffmanTrainer.countFreq (once per chunk) + constructHuffmanTable: returns (encodingTable, state).
+    `state` carries what the reference keeps in CLASS attributes from one trainer to the next in a process (Huffman.py:30-34,
+    158-160): the statistics dict, the class-level deque -- makeHuffmanNodeQueue appends the new leaves to it and then binds
+    a sorted COPY to the instance (:103-108), so the leaves of earlier trainers are still in it and join the next tree --
+    and the code table dict, which is never cleared.  Otherwise literal: dict in first-insertion order (:74-78), stable
+    sort by frequency (:94), escape weight = number of rare codes (:101), queue re-sorted after every join (:118-119),
+    zero = first popped (:226), depth-first zero-then-one table walk (:238-241, a repeated code keeps the last leaf visited)."""
+    if state is None:
+        state = {"statistics": {}, "queue": [], "table": {}}
+    stats = state["statistics"]
+    for chunk in chunks:
+        for c in chunk:
+            c = int(c)
+            stats[c] = stats.get(c, 0) + 1
+    esc = 0
+    for code, freq in sorted(stats.items(), key=lambda t: t[1]):
+        if freq < low_freq:
+            esc += 1
+        else:
+            state["queue"].append([freq, code, None, None])
+    state["queue"].append([esc, escape_code, None, None])
+    queue = sorted(state["queue"], key=lambda t: t[0])
+    while len(queue) > 1:
+        a, b = queue.pop(0), queue.pop(0)
+        queue.append([a[0] + b[0], None, a, b])
+        queue.sort(key=lambda t: t[0])
+    table = state["table"]
+    stack = [(queue[0], "")]
+    while stack:
+        node, code = stack.pop()
+        if node[1] is not None:
+            table[node[1]] = code
+            continue
+        stack.append((node[3], code + "1"))
+        stack.append((node[2], code + "0"))
+    return dict(table), state

@@ -97,6 +97,7 @@ def lib():
     L.pac_huffman_select.argtypes = [vp, C.POINTER(C.c_uint32), i32p, C.c_int, i32p, i64p]
     L.pac_bitalloc.argtypes = [vp, C.c_int, dp, i64p, C.c_int, dp, i32p, i32p, i64p]
     L.pac_bitalloc_alt.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int, dp, i32p]
+    L.pac_histogram.argtypes = [vp, C.c_void_p, C.c_int64, C.c_int64, C.c_int, i64p, i64p]
     L.pac_scale_factor.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, i32p]
     L.pac_vquantize_uniform.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.pac_vdequantize_uniform.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int, C.c_int, dp]
@@ -416,6 +417,18 @@ class Engine(object):
         self._ck(lib().pac_bitalloc(self.ctx, n, _p(bb, C.c_double), _p(eb, C.c_int64), int(maxMantBits), _p(smr, C.c_double),
                                     _p(lm, C.c_int32), _p(bits, C.c_int32), _p(diff, C.c_int64)))
         return bits, diff
+
+    def histogram(self, codes, nbins=1 << 16, base=0):
+        """Huffman.py:71-83 on the device: (counts[nbins], first[nbins]) of unsigned mantissa codes; `codes` is a uint32 numpy
+        array or a CUDA tensor (torch.int32 / uint32 viewed as such).  first = base + index of the first occurrence, -1 if absent."""
+        counts = np.zeros(nbins, np.int64); first = np.zeros(nbins, np.int64)
+        if hasattr(codes, "data_ptr"):
+            ptr, n = C.c_void_p(codes.data_ptr()), int(codes.numel())
+        else:
+            codes = np.ascontiguousarray(codes, np.uint32)
+            ptr, n = codes.ctypes.data_as(C.c_void_p), int(codes.size)
+        self._ck(lib().pac_histogram(self.ctx, ptr, n, int(base), int(nbins), _p(counts, C.c_int64), _p(first, C.c_int64)))
+        return counts, first
 
     def bitalloc_alt(self, mode, bitBudget, maxMantBits, level=None):
         """bitalloc.py:22-125 on n problems; mode 'uniform' | 'constsnr' | 'constmnr'; level [n][nBands] (peak SPL / SMR)"""

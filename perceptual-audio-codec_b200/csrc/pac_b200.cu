@@ -1654,6 +1654,37 @@ extern "C" int pac_bitalloc_alt(PacCtx *ctx, int mode, int n, const double *bitB
     return PAC_OK;
 }
 
+extern "C" int pac_histogram(PacCtx *ctx, const uint32_t *codes, int64_t n, int64_t base, int nbins, int64_t *counts, int64_t *first) {
+    if (!ctx) return PAC_E_ARG;
+    if (n < 0 || nbins <= 0 || !counts || !first || (n > 0 && !codes)) FAIL(PAC_E_ARG, "bad arguments to pac_histogram");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w_misc2.ensure((size_t)nbins * 8)); CK(ctx->w_misc3.ensure((size_t)nbins * 8));
+    CK(cudaMemsetAsync(ctx->w_misc2.p, 0, (size_t)nbins * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->w_misc3.p, 0xff, (size_t)nbins * 8, ctx->stream));
+    if (n > 0) {
+        const uint32_t *d_codes = codes;
+        cudaPointerAttributes at;
+        bool onDevice = cudaPointerGetAttributes(&at, codes) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        if (!onDevice) {
+            CK(ctx->w_misc.ensure((size_t)n * 4));
+            CK(cudaMemcpyAsync(ctx->w_misc.p, codes, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_codes = ctx->w_misc.as<uint32_t>();
+        }
+        int64_t grid = (n + 256 * 64 - 1) / (256 * 64);
+        if (grid > ctx->numSMs * 8) grid = ctx->numSMs * 8;
+        if (grid < 1) grid = 1;
+        k_histogram<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_codes, n, base, nbins, ctx->w_misc2.as<unsigned long long>(),
+                                                             ctx->w_misc3.as<unsigned long long>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(counts, ctx->w_misc2.p, (size_t)nbins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(first, ctx->w_misc3.p, (size_t)nbins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PAC_OK;
+}
+
 // small helper for the element-wise quantiser entry points
 #define ELEMWISE(IN_T, OUT_T, inptr, outptr, n, launch)                                                        \
     do {                                                                                                      \

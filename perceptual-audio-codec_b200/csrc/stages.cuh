@@ -147,6 +147,39 @@ __global__ void k_bitalloc_alt(int n, int mode, const double *bitBudget, int max
     if (lane == 0) status[p] = st;
 }
 
+// Histogram.generateStatistics (Huffman.py:71-83) over n unsigned mantissa codes: occurrences per code and the position of
+// each code's first occurrence (the reference's dict keeps first-insertion order, which decides ties when the trainer sorts
+// by frequency, :93-108).  Small codes dominate (they are the Huffman-coded ones), so each CTA counts codes < kHistLocal in
+// shared memory and merges once; larger codes go straight to global atomics.  Grid-stride, coalesced 16-byte loads.
+constexpr int kHistLocal = 4096;
+__global__ void __launch_bounds__(256)
+k_histogram(const uint32_t *codes, long long n, long long base, int nbins, unsigned long long *counts, unsigned long long *first) {
+    __shared__ unsigned cnt[kHistLocal];
+    __shared__ unsigned fst[kHistLocal];          // first position seen by this CTA, relative to the CTA's first element + 1 (0 = none)
+    for (int i = threadIdx.x; i < kHistLocal; i += blockDim.x) { cnt[i] = 0; fst[i] = 0xffffffffu; }
+    __syncthreads();
+    // each CTA owns one contiguous span so that 32-bit relative positions are enough for the shared-memory minima
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint32_t c = codes[i];
+        if (c < (uint32_t)kHistLocal) {
+            atomicAdd(&cnt[c], 1u);
+            atomicMin(&fst[c], (unsigned)(i - lo));
+        } else if (c < (uint32_t)nbins) {
+            atomicAdd(&counts[c], 1ull);
+            atomicMin(&first[c], (unsigned long long)(base + i));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistLocal && i < nbins; i += blockDim.x) {
+        if (cnt[i]) {
+            atomicAdd(&counts[i], (unsigned long long)cnt[i]);
+            atomicMin(&first[i], (unsigned long long)(base + lo + fst[i]));
+        }
+    }
+}
+
 // Huffman.encodeData (Huffman.py:274-309) on caller-supplied unsigned mantissas: total code length under each of
 // the 10 tables (escape = escape code + bitAlloc raw bits), strictly-shortest wins, ties keep the lowest ID.
 __global__ void k_huff_select(const uint32_t *mag, const int32_t *ba, int n, const unsigned long long *lenLut, EncConsts ec,

@@ -188,6 +188,57 @@ def test_shim_bitalloc_alt(kats, oracle, pb):
     assert [list(r) for r in got] == [c["bits"] for c in kats["bitalloc_alt"] if c["mode"] == "uniform"]
 
 
+def test_shim_huffman_trainer(kats, pb, tmp_path, monkeypatch):
+    """Huffman.py:27-250 with the counting pass on the GPU (pac_histogram): histogram facts vs numpy, then the reference's own
+    tables for two trainers in one process; the pickles in the CWD are extended like the reference does."""
+    import importlib
+    import pickle
+    import shutil
+    import torch
+    import Huffman
+    importlib.reload(Huffman)                                  # fresh class-level state
+    e = pb.engine()
+    rng = np.random.default_rng(3)
+    for n in (1, 257, 100003, 3000000):
+        c = np.minimum(rng.geometric(0.01, n) - 1, 70000).astype(np.uint32)
+        for src in (c, torch.from_numpy(c.astype(np.int32)).cuda()):
+            cnt, first = e.histogram(src, nbins=1 << 16, base=5)
+            want = np.bincount(c[c < 65536], minlength=65536)
+            assert np.array_equal(cnt, want)
+            uniq, idx = np.unique(c, return_index=True)
+            wf = np.full(65536, -1, np.int64)
+            wf[uniq[uniq < 65536]] = idx[uniq < 65536] + 5
+            assert np.array_equal(first, wf)
+    h = kats["huffman_trainer"]
+
+    def codes(seed, n, p):
+        g = np.random.default_rng(seed)
+        c = g.geometric(p, n) - 1
+        c[g.integers(0, n, n // 50)] = g.integers(0, 30000, n // 50)
+        return c
+    for f in ("huffmanTables.pickle", "histograms.pickle"):
+        shutil.copy(pb.find_pickle(f), tmp_path / f)
+    monkeypatch.chdir(tmp_path)
+    f1 = h["first"]
+    c1 = codes(f1["seed"], f1["n"], f1["p"])
+    t1 = Huffman.HuffmanTrainer(11)
+    t1.countFreq(c1[:f1["split"]])
+    t1.countFreq(torch.from_numpy(c1[f1["split"]:].astype(np.int32)).cuda())     # device-resident codes
+    t1.constructHuffmanTable()
+    assert {str(a): b for a, b in t1.huffmanCodeTable.items()} == f1["table"]
+    assert t1.histogram.getMatchScore(Huffman.Histogram()) == 3.0               # the shared dict against itself (Huffman.py:30-31)
+    f2 = h["second"]
+    t2 = Huffman.HuffmanTrainer(12)
+    t2.countFreq([int(v) for v in codes(f2["seed"], f2["n"], f2["p"])])
+    t2.constructHuffmanTable()
+    assert {str(a): b for a, b in t2.huffmanCodeTable.items()} == f2["table"]
+    with open("huffmanTables.pickle", "rb") as fh:
+        stored = pickle.load(fh, encoding="latin1")
+    assert len(stored) == 12 and {str(a): b for a, b in stored[12].encodingTable.items()} == f2["table"]
+    assert stored[12].decodingTable[f2["table"]["0"]] == 0
+    importlib.reload(Huffman)
+
+
 def test_shim_calcsmrs_sixtone(kats):
     """psychoac.py:696-713 through the mono kernel (N = 1024, fs = 48000)."""
     import mdct

@@ -119,6 +119,30 @@ def test_bitalloc_alt_kats(oracle, kats):
         oracle.bitalloc_alt("constmnr", 2116.48, 16, 25, c["nLines"], c["level"])
 
 
+def _trainer_codes(seed, n, p):
+    g = np.random.default_rng(seed)
+    c = g.geometric(p, n) - 1
+    c[g.integers(0, n, n // 50)] = g.integers(0, 30000, n // 50)
+    return c
+
+
+def test_huffman_trainer_kats(kats):
+    """Huffman.py:156-250: the restated trainer reproduces the tables the reference built here, including the second trainer of
+    a process (class-level statistics / queue / table carry over)."""
+    import oracle as orc
+    h = kats["huffman_trainer"]
+    f = h["first"]
+    c1 = _trainer_codes(f["seed"], f["n"], f["p"])
+    t1, st = orc.train_huffman([c1[:f["split"]], c1[f["split"]:]])
+    assert {str(a): b for a, b in t1.items()} == f["table"]
+    g = h["second"]
+    t2, st = orc.train_huffman([_trainer_codes(g["seed"], g["n"], g["p"])], state=st)
+    assert {str(a): b for a, b in t2.items()} == g["table"]
+    # prefix-free, escape present
+    codes = sorted(t1.values())
+    assert all(not codes[i + 1].startswith(codes[i]) for i in range(len(codes) - 1)) and -1 in t1
+
+
 def test_huffman_table_facts(oracle, kats):
     for tid, f in kats["huffman_tables"].items():
         t = oracle.tables[int(tid)]
