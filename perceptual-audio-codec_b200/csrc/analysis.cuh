@@ -15,6 +15,10 @@
 
 #include "fft.cuh"
 
+#ifndef PAC_ANALYSIS_CTAS
+#define PAC_ANALYSIS_CTAS 4      // resident fp32 analysis CTAs per SM the kernel is compiled for (64 registers per thread)
+#endif
+
 namespace pac {
 
 template <typename T>
@@ -42,17 +46,25 @@ struct AnalysisArgs {
     uint32_t poisonOn, poison, smemWords;   // debugging aid (PAC_POISON_SMEM): refill shared memory before every block
 };
 
-// extra shared memory of the fp32 fast threshold evaluation
+// extra shared memory of the fp32 fast threshold evaluation.  The three dense per-bin arrays of a curve (Sp, V, Wq: 16 400 B)
+// are NOT here: they live in whichever spectrum buffer is dead while the curve runs (W during the L/R curves, XF afterwards),
+// which is what lets four CTAs share an SM.
 template <int LOGM>
 struct FastSmem {
     static constexpr int M = 1 << LOGM;
-    double Sp[M + 2];             // exclusive prefix sums (in double) of the plateau intensities A_k over the bins
     double wtot[16];
-    float V[M], Wq[M];            // dense per bin: down-scan injection, up-scan injection (quiet maskers)
     float4 loud[M / 2];           // maskers louder than 40 dB: (B_hi, up, B_lo, first upper-skirt line as int bits) with
                                   // B = c0 - up/2 - up * z_masker formed in double: exponent at line i = up * z_i + B
-    unsigned short loudPrefix[M + 2];   // number of loud maskers with bin < k
+    unsigned short loudBase[M / 4 + 4];   // number of loud maskers below bin 4t ...
+    unsigned char loudFlag[M / 4 + 4];    // ... and which of the bins 4t .. 4t+3 are loud (prefix at any bin = base + popc)
     float totD[16], totA[16];
+};
+// scratch layout inside the dead spectrum buffer
+template <int LOGM>
+struct CurveScratch {
+    static constexpr int M = 1 << LOGM;
+    double Sp[M + 2];             // exclusive prefix sums (in double) of the plateau intensities A_k over the bins
+    float V[M], Wq[M];            // dense per bin: down-scan injection, up-scan injection (quiet maskers)
 };
 struct NoSmem {};
 
@@ -215,7 +227,7 @@ __device__ __forceinline__ float spl_any(float i) { return spl_fast(i); }
 __device__ __forceinline__ double spl_any(double i) { return spl_of<double>(i); }
 
 template <int LOGM>
-__device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, const float2 *F, int tap, float drop,
+__device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, CurveScratch<LOGM> &cs, const float2 *F, int tap, float drop,
                                                  const DevTables<float> *tbp, const FastTables *ftp, const double *zpeakd,
                                                  const double *zlined, int lb0, int lb1, uint32_t kU0, uint32_t kU1) {
     constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
@@ -272,7 +284,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
                     else Wv = ex2_approx(c0 + bt.y);
                 }
             }
-            fs.V[k] = Vv; fs.Wq[k] = Wv;
+            cs.V[k] = Vv; cs.Wq[k] = Wv;
             Aq[q] = Av;
         }
     }
@@ -292,11 +304,12 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
     int offs = incl - nl;
     double dbase = dincl - A3;
     for (int i = 0; i < warp; i++) { offs += sm.wsum[i]; dbase += fs.wtot[i]; }
-    fs.Sp[k0] = dbase; fs.Sp[k0 + 1] = dbase + A0; fs.Sp[k0 + 2] = dbase + A1; fs.Sp[k0 + 3] = dbase + A2;
-    if (tid == NT - 1) fs.Sp[M] = dbase + A3;
+    cs.Sp[k0] = dbase; cs.Sp[k0 + 1] = dbase + A0; cs.Sp[k0 + 2] = dbase + A1; cs.Sp[k0 + 3] = dbase + A2;
+    if (tid == NT - 1) cs.Sp[M] = dbase + A3;
+    fs.loudBase[tid] = (unsigned short)offs;
+    fs.loudFlag[tid] = (unsigned char)loudf;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        fs.loudPrefix[k0 + q] = (unsigned short)offs;
         if (loudf & (1u << q)) {
             const double Bd = ((double)c0s[q] - 0.5 * (double)ups[q]) - (double)ups[q] * ((double)btq[q].z + (double)btq[q].w);
             const float Bh = (float)Bd;
@@ -304,7 +317,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
             offs++;
         }
     }
-    if (tid == NT - 1) { fs.loudPrefix[M] = (unsigned short)offs; fs.loudPrefix[M + 1] = (unsigned short)offs; }
+    if (tid == NT - 1) { fs.loudBase[NT] = (unsigned short)offs; fs.loudFlag[NT] = 0; }
     __syncthreads();
     // 3. per-line gathers (deterministic order) + plateau + the two scans; thread t owns lines 4t .. 4t+3
     {
@@ -313,10 +326,10 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int kLa = lgq[q] & 1023, nL = (lgq[q] >> 10) & 3, kUa = (lgq[q] >> 12) & 1023, nU = (lgq[q] >> 22) & 3;
-            uD[q] = (nL > 0 ? fs.V[kLa] : 0.f) + (nL > 1 ? fs.V[kLa + 1] : 0.f) + (nL > 2 ? fs.V[kLa + 2] : 0.f);
-            uA[q] = (nU > 0 ? fs.Wq[kUa] : 0.f) + (nU > 1 ? fs.Wq[kUa + 1] : 0.f) + (nU > 2 ? fs.Wq[kUa + 2] : 0.f);
+            uD[q] = (nL > 0 ? cs.V[kLa] : 0.f) + (nL > 1 ? cs.V[kLa + 1] : 0.f) + (nL > 2 ? cs.V[kLa + 2] : 0.f);
+            uA[q] = (nU > 0 ? cs.Wq[kUa] : 0.f) + (nU > 1 ? cs.Wq[kUa + 1] : 0.f) + (nU > 2 ? cs.Wq[kUa + 2] : 0.f);
             // plateau: bins within +-.5 Bark of the line = static window [pa, pb)
-            pl[q] = (float)(fs.Sp[lpq[q] >> 16] - fs.Sp[lpq[q] & 0xffffu]);
+            pl[q] = (float)(cs.Sp[lpq[q] >> 16] - cs.Sp[lpq[q] & 0xffffu]);
         }
         // descending scan: low[i] = sum_{j >= i} uD[j] 2^{dn (z_j - z_i)}
         const float *w = ft.sD + tid;
@@ -380,8 +393,10 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
         const float z0 = zz.x, z0l = zz.y;
         const float dz01 = (zz.z - zz.x) + (zz.w - zz.y);          // Bark gap to the lane's second line
         const uint32_t kU = hh ? kU1 : kU0;
-        const int mfull = fs.loudPrefix[kU & 0xffffu];        // upper skirt starts at or before the half-chunk
-        const int mhi = fs.loudPrefix[kU >> 16];              // ... at or before its last line
+        // loud maskers below a bin k = base of its group of four + the loud ones among the group's bins below k
+        auto loudBelow = [&](unsigned k) { return (int)fs.loudBase[k >> 2] + __popc((unsigned)fs.loudFlag[k >> 2] & ((1u << (k & 3u)) - 1u)); };
+        const int mfull = loudBelow(kU & 0xffffu);            // upper skirt starts at or before the half-chunk
+        const int mhi = loudBelow(kU >> 16);                  // ... at or before its last line
         int m = 0;
         for (; m < mfull; m++) {
             const float4 p = fs.loud[m];
@@ -407,11 +422,13 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
 }
 
 template <typename T, int LOGM>
-__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? 3 : 1)
+__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? PAC_ANALYSIS_CTAS : 1)
 k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     using S = AnalysisSmem<T, LOGM, sizeof(T) == 4>;
     using T2 = typename Vec2<T>::type;
     constexpr int M = S::M, N = S::N, NT = S::NT, H = M / 2, NW = NT / 32;
+    // fp32: four CTAs per SM need 4 x (dynamic + 1 KB reserved) <= 228 KB
+    static_assert(sizeof(T) == 8 || sizeof(S) <= 57344, "fp32 analysis must fit four CTAs per SM");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S &sm = *reinterpret_cast<S *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -643,29 +660,37 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         }
         // F2_M, F2_S = Hann-taps of (F1_L +- F1_R)/2   (psychoac.py:549 then :428 again)
         const T2 hw = tb.hann_w, hwc = cconj(tb.hann_w);
-        for (int e = tid; e < 2 * (M + 1); e += NT) {
-            int c = e / (M + 1), k = e - c * (M + 1);
-            T sg = c ? (T)-1 : (T)1;
-            int km = k == 0 ? 1 : k - 1, kp = k == M ? M - 1 : k + 1;
-            T2 f0 = sm.XF[0][k], f1 = sm.XF[1][k];
-            T2 g0 = sm.XF[0][km], g1 = sm.XF[1][km];
-            T2 h0 = sm.XF[0][kp], h1 = sm.XF[1][kp];
-            T2 fc = mk2<T>((f0.x + sg * f1.x) / 2, (f0.y + sg * f1.y) / 2);
-            T2 fm = mk2<T>((g0.x + sg * g1.x) / 2, (g0.y + sg * g1.y) / 2);
-            T2 fp = mk2<T>((h0.x + sg * h1.x) / 2, (h0.y + sg * h1.y) / 2);
-            if (k == 0) fm = cconj(fm);
-            if (k == M) fp = cconj(fp);
-            T2 t = cadd(cmul(hw, fm), cmul(hwc, fp));
-            sm.W[c][k] = mk2<T>((T)0.5 * fc.x - (T)0.25 * t.x, (T)0.5 * fc.y - (T)0.25 * t.y);
-        }
-        __syncthreads();
+        auto computeF2 = [&]() {
+            for (int e = tid; e < 2 * (M + 1); e += NT) {
+                int c = e / (M + 1), k = e - c * (M + 1);
+                T sg = c ? (T)-1 : (T)1;
+                int km = k == 0 ? 1 : k - 1, kp = k == M ? M - 1 : k + 1;
+                T2 f0 = sm.XF[0][k], f1 = sm.XF[1][k];
+                T2 g0 = sm.XF[0][km], g1 = sm.XF[1][km];
+                T2 h0 = sm.XF[0][kp], h1 = sm.XF[1][kp];
+                T2 fc = mk2<T>((f0.x + sg * f1.x) / 2, (f0.y + sg * f1.y) / 2);
+                T2 fm = mk2<T>((g0.x + sg * g1.x) / 2, (g0.y + sg * g1.y) / 2);
+                T2 fp = mk2<T>((h0.x + sg * h1.x) / 2, (h0.y + sg * h1.y) / 2);
+                if (k == 0) fm = cconj(fm);
+                if (k == M) fp = cconj(fp);
+                T2 t = cadd(cmul(hw, fm), cmul(hwc, fp));
+                sm.W[c][k] = mk2<T>((T)0.5 * fc.x - (T)0.25 * t.x, (T)0.5 * fc.y - (T)0.25 * t.y);
+            }
+            __syncthreads();
+        };
+        if constexpr (!FAST) computeF2();
         // ------------------------------------------------ E. six masked-threshold curves
         T thr[6][4];
         if constexpr (FAST) {
-            const float2 *srcs[6] = {sm.XF[0], sm.XF[1], sm.W[0], sm.W[1], sm.W[0], sm.W[1]};
+            // The dense per-bin scratch of a curve lives in the spectrum buffer that is dead at that point: the L and R curves read
+            // F1 from XF while W (the consumed FFT work area) is free; then F2 is formed in W and XF becomes the scratch.
+            static_assert(sizeof(CurveScratch<LOGM>) <= sizeof(sm.W) && sizeof(CurveScratch<LOGM>) <= sizeof(sm.XF), "scratch must fit a spectrum buffer");
 #pragma unroll 1
             for (int c = 0; c < 6; c++) {
-                const float4 r = masked_curve_fast<LOGM>(sm, srcs[c], c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, a.tabd.zpeak, a.tabd.zline,
+                if (c == 2) computeF2();
+                CurveScratch<LOGM> &cs = *reinterpret_cast<CurveScratch<LOGM> *>(c < 2 ? &sm.W[0][0] : &sm.XF[0][0]);
+                const float2 *src = c < 2 ? sm.XF[c] : sm.W[c & 1];
+                const float4 r = masked_curve_fast<LOGM>(sm, cs, src, c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, a.tabd.zpeak, a.tabd.zline,
                                                          lineBase[0], lineBase[1], kU0, kU1);
                 thr[c][0] = r.x; thr[c][1] = r.y; thr[c][2] = r.z; thr[c][3] = r.w;
             }
