@@ -112,12 +112,15 @@ k_pack(const PackArgs<T> a) {
                     else { code = escc; len = escl; code2 = mag; len2 = bab; }      // Huffman.py:296-298
                 }
                 int tl = len + len2;
+                // an escape token (escape code + raw magnitude, Huffman.py:296-298) is written as ONE field when it fits 32 bits
+                // (always with the stock tables: escape codes are <= 13 bits, magnitudes <= 16)
+                if (len2 && tl <= 32) { code = (code << len2) | code2; len = tl; len2 = 0; }
                 int incl = tl;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 unsigned p = pos + (unsigned)(incl - tl);
                 put_bits(buf, p, code, len);
-                put_bits(buf, p + len, code2, len2);
+                if (len2) put_bits(buf, p + len, code2, len2);
                 pos += (unsigned)__shfl_sync(0xffffffffu, incl, 31);
             }
         }

@@ -40,40 +40,48 @@ struct ScanArgs {
 
 // bitalloc.BitAlloc on a warp: lane b < NB owns band b.  Returns this lane's bits; *diff = bitDifference.
 __device__ __forceinline__ unsigned sortable32(float v) {
-    unsigned u = __float_as_uint(v);
-    return (u >> 31) ? ~u : (u | 0x80000000u);
+    const unsigned u = __float_as_uint(v);
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);      // negative: ~u, else u | sign bit (two instructions)
 }
 
-// fp32 fast mode: the SMRs are floats, so the arg-max keys are formed in float (one REDUX per maximum instead of two)
-__device__ __forceinline__ int warp_bitalloc32(double bitBudget, long long extraBits, int maxMantBits, int NB, float smrLane,
-                                               uint32_t lrms, const BandInfo &bands, long long *diff) {
+// fp32 fast mode: the SMRs are floats, so the arg-max keys are formed in float (one REDUX per maximum instead of two).
+// The loop is the serial heart of the scan kernel (about 100 iterations per channel), so it carries its state in the form
+// the next iteration needs: per lane the sortable key of SMR - 6*bits (0 once the band is invalid, so "no valid band
+// left" is simply a zero maximum) and of SMR - 6*(bits-1); only the winning lane's keys change per iteration.  Line
+// counts come from a shuffle of the per-lane count, the bit budget is a 32-bit integer (callers fall back to the generic
+// version for budgets that do not fit).
+__device__ __forceinline__ int warp_bitalloc32(int totalBits0, long long extraBits, int maxMantBits, int NB, float smrLane,
+                                               uint32_t lrms, int nLinesLane, long long *diff) {
     const int lane = threadIdx.x & 31;
     const bool inband = lane < NB;
     int bits = 0;
-    bool valid = inband;
-    long long totalBits = (long long)(bitBudget + (double)extraBits);
+    float fbits = 0.f;
+    int totalBits = totalBits0;
     const unsigned kMS = sortable32(-5.0f), kLR = sortable32(-15.0f);
-    while (__ballot_sync(0xffffffffu, valid) != 0u) {
-        const float v = smrLane - (float)bits * 6.f;
-        const unsigned key = inband ? sortable32(v) : 0u;
-        const unsigned mk1 = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
-        const unsigned win = __ballot_sync(0xffffffffu, valid && key == mk1);
-        const int iMax = __ffs(win) - 1;
-        const unsigned k2 = inband ? sortable32(v + 6.f) : 0u;               // SMR - 6*(bits-1)
+    unsigned vkey = inband ? sortable32(smrLane) : 0u;                     // valid bands only
+    unsigned k2 = inband ? sortable32(smrLane + 6.f) : 0u;                 // all bands: SMR - 6*(bits-1)
+    for (;;) {
+        const unsigned mk1 = __reduce_max_sync(0xffffffffu, vkey);
+        if (mk1 == 0u) break;                                              // no valid band left (bitalloc.py:161)
+        const int iMax = __ffs(__ballot_sync(0xffffffffu, vkey == mk1)) - 1;       // first index wins (np.argmax)
         const unsigned mk2 = __reduce_max_sync(0xffffffffu, k2);
-        const bool below = ((lrms >> iMax) & 1u) ? (mk2 < kMS) : (mk2 < kLR);
-        const int nl = bands.lo[iMax + 1] - bands.lo[iMax];
-        const bool me = lane == iMax;
-        if (below && me) valid = false;
-        if (totalBits - nl >= 0) {
-            totalBits -= nl;
-            if (me) { bits += 1; if (bits >= maxMantBits) valid = false; }
-        } else if (me) valid = false;
+        const bool below = mk2 < (((lrms >> iMax) & 1u) ? kMS : kLR);      // :165-175
+        const int nl = __shfl_sync(0xffffffffu, nLinesLane, iMax);
+        const bool afford = totalBits >= nl;                               // :176
+        if (afford) totalBits -= nl;
+        if (lane == iMax) {
+            bool valid = !below && afford;                                 // invalidated bands still get this iteration's bit (:176-178)
+            if (afford) { bits += 1; fbits += 1.f; if (bits >= maxMantBits) valid = false; }
+            const float v = fmaf(fbits, -6.f, smrLane);
+            vkey = valid ? sortable32(v) : 0u;
+            k2 = sortable32(v + 6.f);
+        }
     }
-    unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);
-    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; totalBits += bands.lo[bnd + 1] - bands.lo[bnd]; }
+    unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);       // bits == 1 -> 0 with refund (:179-180)
+    long long tb = totalBits;
+    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; tb += __shfl_sync(0xffffffffu, nLinesLane, bnd); }
     if (bits == 1) bits = 0;
-    *diff = totalBits - extraBits;
+    *diff = tb - extraBits;
     return bits;
 }
 
@@ -163,7 +171,9 @@ k_scan(const ScanArgs<T> a) {
             double bmaxLane = lane < NB ? (double)a.bmax[wc * kMaxBands + lane] : 0.0;
             long long diff;
             int bits;
-            if constexpr (sizeof(T) == 4) bits = warp_bitalloc32(ec.bitBudget, extraBits, ec.maxMantBits, NB, (float)smrLane, lrms, a.bands, &diff);
+            const long long total0 = (long long)(ec.bitBudget + (double)extraBits);          // int() truncation, bitalloc.py:159
+            if (sizeof(T) == 4 && total0 > -(1ll << 30) && total0 < (1ll << 30))
+                bits = warp_bitalloc32((int)total0, extraBits, ec.maxMantBits, NB, (float)smrLane, lrms, nLinesLane, &diff);
             else bits = warp_bitalloc(ec.bitBudget, extraBits, ec.maxMantBits, NB, nLinesLane, smrLane, lrms, a.bands, &diff);
             extraBits += diff;                                             // codec.py:260
             int sfl = scale_factor(bmaxLane, ec.nScaleBits, bits);       // codec.py:274
