@@ -732,15 +732,28 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     if (cap < hdrB) FAIL(PAC_E_OVERFLOW, "cap smaller than the file header");
     const int64_t workBudget = 1 << 18;                       // (stream, block) items per tile buffer
     int Sg = S;
-    const int64_t stagingLimit = (int64_t)24 << 30;
     const bool staged = !pcmDev || !outDev;
     if (staged) {
+        // Host buffers are staged group by group (double-buffered).  Groups are as LARGE as the staging budget allows: a
+        // group's serial reservoir chain (k_scan, ~50-70 us per block per stream whatever the group size) is only hidden
+        // while the group's own analysis lasts longer, i.e. from a few hundred streams up; eight groups of 256 streams
+        // measured 76 k audio-s/s where the same streams device-resident ran at 101 k.  Two groups from 1024 streams on, so
+        // that the first half's images travel back under the second half's kernels.
+        size_t freeB = 0, totalB = 0;
+        int64_t stagingLimit = (int64_t)24 << 30;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const int64_t held = (int64_t)(ctx->w_pcm.cap + ctx->w_pcm2.cap + ctx->w_out.cap + ctx->w_out2.cap);   // reused, not extra
+            const int64_t avail = ((int64_t)freeB + held) / 2;
+            if (avail < stagingLimit) stagingLimit = avail;
+        }
         int64_t per = (pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap);
         int64_t lim = stagingLimit / (2 * (per > 0 ? per : 1));
         if (lim < 1) lim = 1;
-        int want = S >= 2048 ? S / 8 : (S >= 64 ? (S + 3) / 4 : S);
-        if (trace) want = S;
-        Sg = (int)(want < lim ? want : lim);
+        int nG = (int)((S + lim - 1) / lim);
+        if (nG < 2 && S >= 1024) nG = 2;
+        if (const char *ge = getenv("PAC_STAGE_GROUPS")) { const int f = atoi(ge); if (f > nG) nG = f < S ? f : S; }   // tests: force staging groups
+        if (trace) nG = 1;
+        Sg = (S + nG - 1) / nG;
         if (Sg < 1) Sg = 1;
     }
     if (Sg > 8192) Sg = 8192;

@@ -539,9 +539,16 @@ def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
         for pat in ("0", "ffffffff", "7f7f7f7f"):
             os.environ["PAC_POISON_SMEM"] = pat
             assert eng.encode_batch(batch) == ref, pat
+        os.environ.pop("PAC_POISON_SMEM", None)
+        # host buffers are staged in double-buffered stream groups: the grouping must not show either
+        for groups, tb in (("2", "8"), ("5", "13"), ("24", "100000")):
+            os.environ["PAC_STAGE_GROUPS"] = groups
+            os.environ["PAC_TILE_BLOCKS"] = tb
+            assert eng.encode_batch(batch) == ref, ("groups", groups)
     finally:
         os.environ.pop("PAC_TILE_BLOCKS", None)
         os.environ.pop("PAC_POISON_SMEM", None)
+        os.environ.pop("PAC_STAGE_GROUPS", None)
 
 
 def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
