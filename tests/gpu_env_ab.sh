@@ -1,5 +1,6 @@
 #!/bin/bash
 # gpu_env_ab.sh -- short bench under different experiment environment settings (diagnostic)
+# usage: S=512 SEC=60 bash tests/gpu_env_ab.sh "X=0" "PAC_TILE_BLOCKS=81" ...
 S=${S:-592}; SEC=${SEC:-10}
 mkdir -p gpurun_out
 run() {
@@ -9,7 +10,4 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
 print('%-40s step %.2f ms  analysis %.1f ns/block  %s' % ('$*', d['ms_per_step'], 1e6*r['avg_launch_ms']/r['blocks_per_launch'], r['note'].split(';')[-1]))
 " | tee -a gpurun_out/env_ab.log
 }
-run X=0
-run PAC_EXTRA_SMEM=30000
-run PAC_CARVEOUT_KB=164
-run PAC_CARVEOUT_KB=196
+for setting in "$@"; do run $setting; done
