@@ -269,7 +269,16 @@ struct SynthSmem {
     T v[2][M];                   // DCT-IV output
     uint16_t meta[2][kMaxBands];
     float gain[2][kMaxBands];    // fp32 mode: 2/(2^R-1) * 2^(largestScale-sf-1-overallScale) per band
+    // double-buffered cp.async landing area: block b+1's codes and band metadata arrive while block b is transformed
+    __align__(16) uint16_t codes[2][2][M];
+    __align__(16) uint16_t metaRaw[2][2 * kMaxBands];
 };
+
+__device__ __forceinline__ void cp_async16(void *smemDst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // PCMFile.WriteDataBlock quantisation (pcmfile.py:127-134, quantize.py:91-117 with 16 bits)
 __device__ __forceinline__ int pcm16(double v) {
@@ -285,12 +294,12 @@ __device__ __forceinline__ int pcm16(float v) {          // fp32 mode: within 1 
 
 // one dequantised line (codec.py:31-43, quantize.py:345-376)
 template <typename T, typename SS>
-__device__ __forceinline__ T synth_line(const SynthArgs<T> &a, const SS &sm, int64_t chunk, int ch, int i, int bd, double rescale) {
+__device__ __forceinline__ T synth_line(const SynthArgs<T> &a, const SS &sm, int64_t chunk, int ch, int i, int bd, double rescale, int buf) {
     if (!a.codes) return a.lines[chunk * SS::M + i];
     const uint32_t mt = sm.meta[ch][bd];
     const int ba = (int)(mt >> 8), sf = (int)(mt & 0xff);
     if (!ba) return (T)0;
-    const uint32_t code = a.codes[chunk * SS::M + i];
+    const uint32_t code = sm.codes[buf][ch][i];
     if constexpr (sizeof(T) == 8) {
         return (T)(dequant(sf, (long long)code, a.largestScale, ba) * rescale);
     } else {
@@ -330,22 +339,46 @@ k_synth(const SynthArgs<T> a) {
     T ola[4][2];                                                         // overlap tail of samples tid + NT*j (this thread's own)
 #pragma unroll
     for (int j = 0; j < 4; j++) ola[j][0] = ola[j][1] = (T)0;
+    // block b+1's codes (4 KB: one 16-byte cp.async per thread) and band metadata travel while block b is transformed; its
+    // LRMS mask and overall scales are ordinary loads issued one iteration ahead
+    auto prefetch = [&](int b, int buf) {
+        const int64_t w = (int64_t)s * a.maxBlocks + b;
+        cp_async16(&sm.codes[buf][0][0] + 8 * tid, a.codes + w * 2 * M + 8 * tid);
+        if (tid < (2 * kMaxBands * 2) / 16) cp_async16(&sm.metaRaw[buf][0] + 8 * tid, a.meta + w * 2 * kMaxBands + 8 * tid);
+        cp_async_commit();
+    };
+    uint32_t lrmsNext = 0, oscNext = 0;
+    if (bFirst <= bLast) {
+        const int64_t w = (int64_t)s * a.maxBlocks + bFirst;
+        if (a.codes) { prefetch(bFirst, 0); oscNext = (uint32_t)a.oscale[w * 2] | (uint32_t)a.oscale[w * 2 + 1] << 8; }
+        lrmsNext = a.lrms[w];
+    }
     for (int b = bFirst; b <= bLast; b++) {
         const int64_t w = (int64_t)s * a.maxBlocks + b;
-        const uint32_t lrms = a.lrms[w];
+        const uint32_t lrms = lrmsNext;
+        const int osc0 = (int)(oscNext & 0xffu), osc1 = (int)(oscNext >> 8);
+        const int buf = (b - bFirst) & 1;
         double r0 = 1.0, r1 = 1.0;
+        if (a.codes) {
+            cp_async_wait_all();
+            __syncthreads();                       // this block's codes/metadata have landed; the other buffer's readers are done
+        }
+        if (b < bLast) {
+            if (a.codes) { prefetch(b + 1, buf ^ 1); oscNext = (uint32_t)a.oscale[(w + 1) * 2] | (uint32_t)a.oscale[(w + 1) * 2 + 1] << 8; }
+            lrmsNext = a.lrms[w + 1];
+        }
         if (a.codes) {
             if (tid < 2 * kMaxBands) {
                 const int ch = tid / kMaxBands, bd = tid % kMaxBands;
-                const uint32_t mt = a.meta[w * 2 * kMaxBands + tid];
+                const uint32_t mt = sm.metaRaw[buf][tid];
                 sm.meta[ch][bd] = (uint16_t)mt;
                 if (sizeof(T) == 4) {
                     const int ba = (int)(mt >> 8), sf = (int)(mt & 0xff);
                     const double largest = (double)(1ll << ((ba + a.largestScale) & 63)) - 1.0;
-                    sm.gain[ch][bd] = (float)ldexp(2.0 / largest, a.largestScale - sf - 1 - (int)a.oscale[w * 2 + ch]);
+                    sm.gain[ch][bd] = (float)ldexp(2.0 / largest, a.largestScale - sf - 1 - (ch ? osc1 : osc0));
                 }
             }
-            r0 = 1.0 / (double)(1 << a.oscale[w * 2]); r1 = 1.0 / (double)(1 << a.oscale[w * 2 + 1]);   // exact powers of two
+            r0 = 1.0 / (double)(1 << osc0); r1 = 1.0 / (double)(1 << osc1);   // exact powers of two
             __syncthreads();
         }
         // load (+ dequantise) + M/S recombination with the reference's aliasing (codec.py:46-56: L' = M - S,
@@ -353,8 +386,8 @@ k_synth(const SynthArgs<T> a) {
         for (int n = tid; n < H; n += NT) {
             const int iA = 2 * n, iB = M - 1 - 2 * n;
             const int bA = tb.band_of_line[iA], bB = tb.band_of_line[iB];
-            T a0 = synth_line<T, SS>(a, sm, w * 2, 0, iA, bA, r0), a1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iA, bA, r1);
-            T b0 = synth_line<T, SS>(a, sm, w * 2, 0, iB, bB, r0), b1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iB, bB, r1);
+            T a0 = synth_line<T, SS>(a, sm, w * 2, 0, iA, bA, r0, buf), a1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iA, bA, r1, buf);
+            T b0 = synth_line<T, SS>(a, sm, w * 2, 0, iB, bB, r0, buf), b1 = synth_line<T, SS>(a, sm, w * 2 + 1, 1, iB, bB, r1, buf);
             if ((lrms >> bA) & 1u) { a0 = a0 - a1; a1 = a0 + a1; }
             if ((lrms >> bB) & 1u) { b0 = b0 - b1; b1 = b0 + b1; }
             const T2 pre = tb.mdct_pre[n];
