@@ -258,8 +258,10 @@ def curve_v2(T, G, F, drop, dtype=np.float32, stats=None):
     npairs = 0
     for kk, c0, up in loud:
         i0 = G.eU[kk]
-        dz = (zl[i0:] - T.zpeak[kk] - 0.5)           # formed from hi+lo pairs in the kernel: exact to ~1e-9 Bark
-        e = (c0 + up * dz.astype(dtype)).astype(dtype)
+        # the kernel forms B = c0 - up/2 - up * z_masker once per masker in double (split hi + lo) and evaluates the exponent at
+        # line i as fma(up, z_i.hi, B.hi) + fma(up, z_i.lo, B.lo): the double expression below rounded once
+        B = np.float64(c0) - 0.5 * np.float64(up) - np.float64(up) * T.zpeak[kk]
+        e = (np.float64(up) * zl[i0:] + B).astype(dtype)
         acc[i0:] += (2.0 ** e.astype(np.float64)).astype(dtype)
         npairs += M - i0
     if stats is not None:
