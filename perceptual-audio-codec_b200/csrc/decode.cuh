@@ -314,7 +314,7 @@ __device__ __forceinline__ T synth_line(const SynthArgs<T> &a, const SS &sm, int
 }
 
 template <typename T, int LOGM>
-__global__ void __launch_bounds__((1 << LOGM) / 4)
+__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? 6 : 1)
 k_synth(const SynthArgs<T> a) {
     using SS = SynthSmem<T, LOGM>;
     using T2 = typename Vec2<T>::type;
