@@ -699,6 +699,12 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
 template <typename T>
 static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
     a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.codeLut = ctx->codeFlat; a.lenLutFlat = ctx->lenFlat;
+    {
+        DevTables<T> tb;
+        int rc = get_tables<T>(ctx, ctx->N, &tb);
+        if (rc) return rc;
+        a.band_of_line = tb.band_of_line;
+    }
     int64_t nchunks = (int64_t)a.S * a.nb * 2;
     int64_t grid = (nchunks + kPackWarps - 1) / kPackWarps;
     int64_t maxg = (int64_t)ctx->numSMs * 8;

@@ -1,8 +1,17 @@
 // pack.cuh -- K5: one warp per (stream, block, channel) chunk re-quantises the selected lines with the
 // allocation K4 fixed, Huffman-codes them with the chosen table and packs the MSB-first bit stream
 // (PACFile.WriteDataBlock pacfile.py:319-351, PackedBits.WriteBits bitpack.py:36-101, StripSignBits
-// codec.py:67-81, escape coding Huffman.py:292-298).  Bit positions inside a chunk come from a warp-level
-// exclusive prefix sum of the code lengths; the chunk's byte offset inside the stream image was fixed by K4.
+// codec.py:67-81, escape coding Huffman.py:292-298).  The chunk's byte offset inside the stream image was fixed by K4.
+//
+// Layout of a chunk (pacfile.py:324-348): [overallScale][tableID] then per band [ba-1][sf][nLines sign bits][tokens],
+// then the LRMS bits.  With P(i) = number of token bits of all lines before line i (ONE running prefix over the whole
+// chunk), every field's position is a per-band constant plus a value of P:
+//     header of band b   S[b] + P(lo_b)            S[b] = chunk header + sum over b' < b of (band header + sign bits)
+//     sign bit of line i S[b] + hdr + P(lo_b) + (i - lo_b)
+//     token of line i    S[b] + hdr + signs_b + P(i)
+// so the lines are walked flat, 32 per step whatever the band widths (the 17 narrowest bands hold 4..26 lines each),
+// with one warp prefix sum per step; sign runs are emitted by the first lane of each band segment of a step, band
+// headers by lane = band at the end.
 #pragma once
 #include "common.cuh"
 
@@ -24,6 +33,7 @@ struct PackArgs {
     long long cap;
     int perChunk;                     // 1: per-block API, payload only, at out + (w*2+ch)*cap
     int *overflow;                    // [S] set to 1 when a chunk would not fit
+    const uint8_t *band_of_line;      // [M]
     const uint32_t *codeLut;          // flattened code values   (PacHuffTables.code)
     const uint8_t *lenLutFlat;        // flattened code lengths  (PacHuffTables.len)
     int32_t *o_mant;                  // optional [nchunk][M] signed mantissa codes at line positions (pre-zeroed)
@@ -52,7 +62,12 @@ k_pack(const PackArgs<T> a) {
     const int NB = a.bands.nBands, M = a.M;
     const EncConsts &ec = a.ec;
     const int largestScale = (1 << ec.nScaleBits) - 1;
+    const int hdrBits = ec.nMantSizeBits + ec.nScaleBits;
+    const int nGroups = M / 32;                          // M is 512 or 1024
     unsigned *buf = sbuf[warp];
+    // static, lane = band: the band's first line and width
+    const int loLane = lane < NB ? a.bands.lo[lane] : M;
+    const int nlLane = lane < NB ? a.bands.lo[lane + 1] - a.bands.lo[lane] : 0;
 
     for (int64_t c = (int64_t)blockIdx.x * kPackWarps + warp; c < nchunks; c += (int64_t)gridDim.x * kPackWarps) {
         const int64_t w = c >> 1;
@@ -67,65 +82,85 @@ k_pack(const PackArgs<T> a) {
         const unsigned nwords = (nby + 3) >> 2;
         if (nwords > (unsigned)kChunkWords) { if (lane == 0 && a.overflow) a.overflow[s] = 1; continue; }
         for (unsigned i = lane; i < nwords + 2; i += 32) buf[i] = 0;
-        __syncwarp();
         const int tid = a.tableID[c] - 1;
         const int off_t = ec.off[tid], nkeys_t = ec.nkeys[tid];
         const unsigned escc = ec.esc_code[tid];
         const int escl = ec.esc_len[tid];
         const T *x = a.lines + c * M;
-        unsigned pos = 0;
+        // lane = band: allocation, scale factor, and S[b] (exclusive prefix of band header + sign bits)
+        const int babL = lane < NB ? a.ba[c * kMaxBands + lane] : 0, sfL = lane < NB ? a.sf[c * kMaxBands + lane] : 0;
+        const unsigned pbL = (unsigned)babL | (unsigned)sfL << 8;
+        const int fixedL = lane < NB ? hdrBits + (babL ? nlLane : 0) : 0;
+        int inclS = fixedL;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inclS, o); if (lane >= o) inclS += v; }
+        const int pos0 = ec.nScaleBits + ec.nTableIDBits;
+        const int SL = pos0 + inclS - fixedL;                              // S[b]
+        const int CsgnL = SL + hdrBits, CtokL = SL + fixedL;               // sign run / token area of band b, before adding P
+        const int fixedTotal = pos0 + __shfl_sync(0xffffffffu, inclS, 31);
+        int PbandL = -1;                                                   // P(lo_b), filled in when the walk reaches the band
+        __syncwarp();
+        int carry = 0;                                                     // token bits of all lines before this step
+        for (int g = 0; g < nGroups; g++) {
+            const int i0 = 32 * g, i = i0 + lane;
+            const int bd = a.band_of_line[i];
+            const unsigned pb = __shfl_sync(0xffffffffu, pbL, bd);
+            const int bab = (int)(pb & 0xff), sfb = (int)(pb >> 8);
+            const T xv = x[i];
+            unsigned code = 0, code2 = 0;
+            int len = 0, len2 = 0;
+            bool sg = false;
+            if (bab) {
+                sg = signbit((double)xv);                                  // np.signbit semantics (quantize.py:333): -0.0 counts
+                const unsigned mag = mant_mag(fabs((double)xv), sfb, largestScale, bab);
+                if (a.o_mant) a.o_mant[c * M + i] = (int32_t)(mag + (sg ? (1u << (bab - 1)) : 0u));
+                const int l = (int)mag < nkeys_t ? a.lenLutFlat[off_t + mag] : 0;
+                if (l) { code = a.codeLut[off_t + mag]; len = l; }
+                else { code = escc; len = escl; code2 = mag; len2 = bab; }      // Huffman.py:296-298
+            }
+            int tl = len + len2;
+            // an escape token (escape code + raw magnitude) is written as ONE field when it fits 32 bits (always with the
+            // stock tables: escape codes are <= 13 bits, magnitudes <= 16)
+            if (len2 && tl <= 32) { code = (code << len2) | code2; len = tl; len2 = 0; }
+            int incl = tl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int P = carry + incl - tl;                                // P(i)
+            // bands that start inside this step learn their P(lo_b)
+            {
+                const int v = __shfl_sync(0xffffffffu, P, (loLane - i0) & 31);
+                if (loLane >= i0 && loLane < i0 + 32) PbandL = v;
+            }
+            // tokens (:337-341)
+            const unsigned tp = (unsigned)(__shfl_sync(0xffffffffu, CtokL, bd) + P);
+            put_bits(buf, tp, code, len);
+            if (len2) put_bits(buf, tp + len, code2, len2);
+            // sign bits of the whole band come first (:335-336): the first lane of each band segment of this step writes the run
+            const unsigned bal = __ballot_sync(0xffffffffu, sg);
+            const int bdPrev = __shfl_up_sync(0xffffffffu, bd, 1);
+            const int loB = __shfl_sync(0xffffffffu, loLane, bd), nlB = __shfl_sync(0xffffffffu, nlLane, bd);
+            const int csg = __shfl_sync(0xffffffffu, CsgnL, bd), pband = __shfl_sync(0xffffffffu, PbandL, bd);
+            if (bab && (lane == 0 || bd != bdPrev)) {
+                int n = loB + nlB - i;                                      // lines of this band from i on ...
+                if (n > 32 - lane) n = 32 - lane;                           // ... that belong to this step
+                const unsigned run = __brev(bal >> lane) >> (32 - n);       // line i first (MSB-first stream)
+                put_bits(buf, (unsigned)(csg + pband + (i - loB)), run, n);
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane < NB && PbandL < 0) PbandL = carry;                        // bands without lines
+        // band headers (:329-332), lane = band
+        if (lane < NB) {
+            const unsigned baF = (unsigned)(babL ? babL - 1 : 0) & ((1u << ec.nMantSizeBits) - 1u);
+            const unsigned sfF = (unsigned)sfL & ((1u << ec.nScaleBits) - 1u);
+            put_bits(buf, (unsigned)(SL + PbandL), (baF << ec.nScaleBits) | sfF, hdrBits);
+        }
         if (lane == 0) {
             put_bits(buf, 0, a.oscale[c], ec.nScaleBits);                       // pacfile.py:324
             put_bits(buf, ec.nScaleBits, (unsigned)(tid + 1), ec.nTableIDBits);  // :326
+            // LRMS: band 0 first (:347-348) -> bit-reverse the mask into MSB-first order
+            put_bits(buf, (unsigned)(fixedTotal + carry), __brev(a.lrms[w]) >> (32 - NB), NB);
         }
-        pos = ec.nScaleBits + ec.nTableIDBits;
-        for (int bd = 0; bd < NB; bd++) {
-            const int bab = a.ba[c * kMaxBands + bd], sfb = a.sf[c * kMaxBands + bd];
-            if (lane == 0) {
-                put_bits(buf, pos, (unsigned)(bab ? bab - 1 : 0), ec.nMantSizeBits);   // :329-331
-                put_bits(buf, pos + ec.nMantSizeBits, (unsigned)sfb, ec.nScaleBits);   // :332
-            }
-            pos += ec.nMantSizeBits + ec.nScaleBits;
-            if (!bab) continue;
-            const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
-            // sign bits of the whole band first (:335-336), np.signbit semantics (quantize.py:333)
-            for (int i0 = lo; i0 < hi; i0 += 32) {
-                int i = i0 + lane;
-                bool sg = false;
-                if (i < hi) sg = signbit((double)x[i]);
-                unsigned bal = __ballot_sync(0xffffffffu, sg);
-                int n = min(32, hi - i0);
-                if (lane == 0) put_bits(buf, pos, __brev(bal) >> (32 - n), n);
-                pos += n;
-            }
-            // then the Huffman tokens (:337-341)
-            for (int i0 = lo; i0 < hi; i0 += 32) {
-                int i = i0 + lane;
-                unsigned code = 0;
-                int len = 0, len2 = 0;
-                unsigned code2 = 0;
-                if (i < hi) {
-                    unsigned mag = mant_mag(fabs((double)x[i]), sfb, largestScale, bab);
-                    if (a.o_mant) a.o_mant[c * M + i] = (int32_t)(mag + (signbit((double)x[i]) ? (1u << (bab - 1)) : 0u));
-                    int l = (int)mag < nkeys_t ? a.lenLutFlat[off_t + mag] : 0;
-                    if (l) { code = a.codeLut[off_t + mag]; len = l; }
-                    else { code = escc; len = escl; code2 = mag; len2 = bab; }      // Huffman.py:296-298
-                }
-                int tl = len + len2;
-                // an escape token (escape code + raw magnitude, Huffman.py:296-298) is written as ONE field when it fits 32 bits
-                // (always with the stock tables: escape codes are <= 13 bits, magnitudes <= 16)
-                if (len2 && tl <= 32) { code = (code << len2) | code2; len = tl; len2 = 0; }
-                int incl = tl;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                unsigned p = pos + (unsigned)(incl - tl);
-                put_bits(buf, p, code, len);
-                if (len2) put_bits(buf, p + len, code2, len2);
-                pos += (unsigned)__shfl_sync(0xffffffffu, incl, 31);
-            }
-        }
-        // LRMS: band 0 first (:347-348) -> bit-reverse the mask into MSB-first order
-        if (lane == 0) put_bits(buf, pos, __brev(a.lrms[w]) >> (32 - NB), NB);
         __syncwarp();
         // ---- store: [<L nBytes][payload] at the offset K4 assigned
         uint8_t *dst;
