@@ -647,8 +647,6 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     if (const char *ex = getenv("PAC_EXTRA_SMEM")) smem += (size_t)atoi(ex);      // occupancy experiments
     a.poisonOn = 0; a.poison = 0; a.smemWords = (uint32_t)(sizeof(AnalysisSmem<T, LOGM, sizeof(T) == 4>) / 4);
     if (const char *po = getenv("PAC_POISON_SMEM")) { a.poisonOn = 1; a.poison = (uint32_t)strtoul(po, nullptr, 16); }
-    static bool configured[2] = {false, false};
-    (void)configured;
     CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (const char *cv = getenv("PAC_CARVEOUT_KB"))                                // L1-size experiments
         CK(cudaFuncSetAttribute(k_analysis<T, LOGM>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv) * 100 / 228));
@@ -717,7 +715,7 @@ static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
 }
 
 // ------------------------------------------------------------------ encode (whole streams)
-// Schedule.  Streams are cut into groups (host buffers: about eight, so that copies pipeline; device buffers: one),
+// Schedule.  Streams are cut into groups (host buffers: as few as the staging budget allows, two from 1024 streams on; device buffers: one),
 // a group into time tiles of TB blocks.  Three internal CUDA streams:
 //   sA (low priority)   k_analysis of every tile, in order
 //   sB (high priority)  k_scan + k_pack of every tile, in order, one tile behind sA (double-buffered intermediates)
