@@ -397,7 +397,7 @@ def main():
                     + ", ".join("%s %.1f ms" % (k, v[0]) for k, v in tm.items() if v[1])}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:       # the CPU port is timed beside the N=1 run only
         cores = os.cpu_count() or 1
         sec = args.ref_seconds
         sample_ids = list(range(cores))
