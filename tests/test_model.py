@@ -57,3 +57,52 @@ def test_scan_based_curve_matches_direct_evaluation(stages):
             worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - ref))))
     print("worst |dB error|", worst, stats)
     assert worst <= 1e-4
+
+
+def test_flat_pack_positions_equal_sequential_layout():
+    """k_pack places every field of a chunk from ONE running token-bit prefix P (csrc/pack.cuh): header of band b at S[b] + P(lo_b),
+    its sign run at S[b] + hdr + P(lo_b), the token of line i at S[b] + hdr + signs_b + P(i), the LRMS bits after everything.
+    Checked here against the layout written band after band as PACFile.WriteDataBlock does (pacfile.py:324-348), for random band
+    layouts including empty bands, zero-bit bands and 32 bands."""
+    rng = np.random.default_rng(8)
+    for trial in range(200):
+        NB = int(rng.integers(1, 33))
+        M = int(rng.choice([512, 1024]))
+        cuts = np.sort(rng.integers(0, M + 1, NB - 1)) if NB > 1 else np.array([], int)
+        lo = np.concatenate([[0], cuts, [M]]).astype(int)                     # lo[b] .. lo[b+1]-1, empty bands allowed
+        nl = np.diff(lo)
+        ba = rng.integers(0, 17, NB)
+        ba[ba == 1] = 0
+        if trial % 5 == 0:
+            ba[:] = 0
+        hdr, pos0 = 8, 8
+        tok = np.zeros(M, int)
+        for b in range(NB):
+            if ba[b]:
+                tok[lo[b]:lo[b + 1]] = rng.integers(1, 38, nl[b])            # code length, escapes up to 37 bits
+        # sequential layout
+        pos = pos0
+        want_hdr, want_sgn, want_tok = np.zeros(NB, int), np.full(NB, -1), np.full(M, -1)
+        for b in range(NB):
+            want_hdr[b] = pos
+            pos += hdr
+            if not ba[b]:
+                continue
+            want_sgn[b] = pos
+            pos += nl[b]
+            for i in range(lo[b], lo[b + 1]):
+                want_tok[i] = pos
+                pos += tok[i]
+        want_lrms = pos
+        # flat evaluation
+        fixed = hdr + np.where(ba > 0, nl, 0)
+        S = pos0 + np.concatenate([[0], np.cumsum(fixed)[:-1]])
+        P = np.concatenate([[0], np.cumsum(tok)])                              # P[i] = token bits before line i; P[M] = total
+        got_hdr = S + P[lo[:-1]]
+        assert np.array_equal(got_hdr, want_hdr)
+        for b in range(NB):
+            if ba[b]:
+                assert S[b] + hdr + P[lo[b]] == want_sgn[b]
+                i = np.arange(lo[b], lo[b + 1])
+                assert np.array_equal(S[b] + fixed[b] + P[i], want_tok[i])
+        assert pos0 + fixed.sum() + P[M] == want_lrms
