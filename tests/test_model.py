@@ -106,3 +106,68 @@ def test_flat_pack_positions_equal_sequential_layout():
                 i = np.arange(lo[b], lo[b + 1])
                 assert np.array_equal(S[b] + fixed[b] + P[i], want_tok[i])
         assert pos0 + fixed.sum() + P[M] == want_lrms
+
+
+def _sortable32(v):
+    u = np.float32(v).view(np.uint32)
+    return int(~u & 0xffffffff) if (int(u) >> 31) else int(u | 0x80000000)
+
+
+def test_incremental_bitalloc_loop_equals_plain_restatement():
+    """The fp32 water-filling loop of k_scan (csrc/scan.cuh: warp_bitalloc32) carries per-band sortable keys between iterations and
+    exits on a zero maximum; here its control flow is replayed in numpy float32 against a plain float32 restatement of
+    bitalloc.BitAlloc (bitalloc.py:129-184): same bits and same bitDifference for random SMRs, budgets, reservoirs and LRMS masks."""
+    rng = np.random.default_rng(12)
+    nl = np.array([5, 4, 5, 5, 5, 5, 7, 7, 7, 9, 10, 11, 13, 15, 17, 21, 26, 32, 42, 51, 61, 83, 116, 163, 304])
+    NB, maxMant = len(nl), 16
+    f32 = np.float32
+    for trial in range(300):
+        smr = rng.uniform(-60, 50, NB).astype(f32)
+        if trial % 9 == 0:
+            smr[:] = smr[0]                                                   # ties: first index wins
+        if trial % 11 == 0:
+            smr[rng.integers(0, NB, 3)] = f32(-96)
+        lrms = rng.integers(0, 2, NB)
+        extra = int(rng.integers(-400, 4000))
+        total0 = int(2116.48 + extra)
+        # plain restatement (float32 arithmetic as the kernel's: v = fma(bits, -6, smr))
+        bits = np.zeros(NB, int); valid = np.ones(NB, bool); total = total0
+        while valid.any():
+            v = (smr - f32(6) * bits.astype(f32)).astype(f32)
+            cand = np.where(valid, v, f32(-np.inf))
+            iMax = int(np.argmax(cand))
+            mx = f32(np.max((v + f32(6)).astype(f32)))
+            if mx < (f32(-5) if lrms[iMax] else f32(-15)):
+                valid[iMax] = False
+            if total - nl[iMax] >= 0:
+                bits[iMax] += 1; total -= nl[iMax]
+                if bits[iMax] >= maxMant:
+                    valid[iMax] = False
+            else:
+                valid[iMax] = False
+        total += nl[bits == 1].sum(); bits[bits == 1] = 0
+        want = (bits.copy(), total - extra)
+        # the kernel's loop
+        bits = np.zeros(NB, int); total = total0
+        vkey = [_sortable32(x) for x in smr]
+        k2 = [_sortable32(f32(x) + f32(6)) for x in smr]
+        kMS, kLR = _sortable32(-5.0), _sortable32(-15.0)
+        while True:
+            mk1 = max(vkey)
+            if mk1 == 0:
+                break
+            iMax = vkey.index(mk1)
+            below = max(k2) < (kMS if lrms[iMax] else kLR)
+            afford = total >= nl[iMax]
+            if afford:
+                total -= nl[iMax]
+            ok = (not below) and afford
+            if afford:
+                bits[iMax] += 1
+                if bits[iMax] >= maxMant:
+                    ok = False
+            v = f32(np.float32(smr[iMax]) - f32(6) * f32(bits[iMax]))
+            vkey[iMax] = _sortable32(v) if ok else 0
+            k2[iMax] = _sortable32(f32(v + f32(6)))
+        total += nl[bits == 1].sum(); bits[bits == 1] = 0
+        assert np.array_equal(bits, want[0]) and total - extra == want[1], trial
