@@ -87,8 +87,12 @@ int  pac_band_layout(PacCtx *ctx, int32_t *nLines /*[PAC_MAX_BANDS]*/, int32_t *
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pac_launch_count(PacCtx *ctx);
 
-/* run this context's kernels and copies on the caller's CUDA stream (a cudaStream_t; NULL = the context's own stream),
- * so that the caller's CUDA events bracket the work. */
+/* run this context's kernels and copies on the caller's CUDA stream (a cudaStream_t), so that the caller's CUDA events
+ * bracket the work and work the caller has queued on that stream (e.g. the kernel that produced a device-resident
+ * input) is ordered before the library's.  A NULL handle means what it means to CUDA: the legacy default stream
+ * (torch's default stream reports handle 0) -- it is mapped to cudaStreamLegacy, NOT to a private stream.
+ * PAC_STREAM_OWN restores the context's own non-blocking stream (the state after pac_ctx_create). */
+#define PAC_STREAM_OWN ((void *)(intptr_t)-1)
 int pac_set_stream(PacCtx *ctx, void *stream);
 
 /* per-kernel device time, measured with CUDA events on the stream the kernels are launched on (bench.py's roofline).
@@ -116,7 +120,8 @@ int64_t pac_encode_bound(PacCtx *ctx, int64_t nSamples);
  *   (Huffman.py:274-309) -> PackedBits.WriteBits (bitpack.py:36-101), plus WriteFileHeader (pacfile.py:231-271)
  *   and the flush block of Close (pacfile.py:355-366).
  * pcm: interleaved int16 [S][strideSamples][2], host or device.  nSamples[s] <= strideSamples (host).
- * out: [S][cap] bytes, host or device; outBytes[s] (host) = bytes of stream s's complete .pac file image.
+ * out: [S][cap] bytes, host or device; outBytes[s] (host) = bytes of stream s's complete .pac file image.  Only
+ *      out[s][0 .. outBytes[s]) is defined afterwards: the rest of a row is left as it was.
  * finalState (host, may be NULL): [S][2] = (huffman.bitDeposit, cp.extraBits) at end of stream. */
 int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S,
                      uint8_t *out, int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace);
@@ -124,7 +129,9 @@ int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, con
 /* replaces the Decode pass of pacfile.py:430-499: PACFile.ReadFileHeader/ReadDataBlock (pacfile.py:123-229),
  * Huffman.decodeData (Huffman.py:321-344), codec.Decode (codec.py:25-65), overlap-add, first block dropped
  * (pacfile.py:485-487), tail emitted (:171-176), PCMFile.WriteDataBlock quantisation (pcmfile.py:118-147).
- * pac: concatenated file images, stream s = pac[pacOff[s] .. pacOff[s+1]) (pacOff host; pac host or device).
+ * pac: concatenated file images, stream s = pac[pacOff[s] .. pacOff[s+1]) (pacOff host; pac host or device).  A DEVICE
+ *      buffer is read in aligned 16-byte granules, so it must sit in an allocation that extends to the next multiple of
+ *      16 bytes past the last image (any cudaMalloc'd buffer does); host images are staged by the library.
  * pcm: interleaved int16 [S][strideSamples][2], host or device; nSamplesOut[s] (host) = samples/channel written;
  * hdrNumSamples/hdrSampleRate (host, may be NULL) = header fields (the WAV header uses them, pcmfile.py:103-116). */
 int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,

@@ -109,12 +109,12 @@ class HuffmanTrainer:                                # Huffman.py:156-250
         self._buildEncodingTree()
         self._buildEncodingTable()
         with open('huffmanTables.pickle', 'rb') as handle:
-            huffmanTables = pickle.load(handle, encoding="latin1")
+            huffmanTables = _pacb200.safe_load(handle, _FIXTURE_CLASSES)
         huffmanTables[self.tableID] = HuffmanTable(self.huffmanCodeTable)
         with open('huffmanTables.pickle', 'wb') as handle:
             pickle.dump(huffmanTables, handle, protocol=0)
         with open('histograms.pickle', 'rb') as handle:
-            histograms = pickle.load(handle, encoding="latin1")
+            histograms = _pacb200.safe_load(handle, _FIXTURE_CLASSES)
         histograms[self.tableID] = self.histogram
         with open('histograms.pickle', 'wb') as handle:
             pickle.dump(histograms, handle, protocol=0)
@@ -143,12 +143,15 @@ class HuffmanTrainer:                                # Huffman.py:156-250
             stack.append((node.zero, code + "0"))
 
 
+_FIXTURE_CLASSES = {"HuffmanTable": HuffmanTable, "Histogram": Histogram, "HuffmanNode": HuffmanNode}
+
+
 class Huffman:
     def __init__(self):
         with open(_pacb200.find_pickle('huffmanTables.pickle'), 'rb') as handle:        # Huffman.py:257-258
-            self.huffmanTables = pickle.load(handle, encoding="latin1")
+            self.huffmanTables = _pacb200.safe_load(handle, _FIXTURE_CLASSES)
         with open(_pacb200.find_pickle('histograms.pickle'), 'rb') as handle:           # :259-260
-            self.histograms = pickle.load(handle, encoding="latin1")
+            self.histograms = _pacb200.safe_load(handle, _FIXTURE_CLASSES)
         self.ESCAPE_CODE = -1
         self.bitDeposit = 0
 

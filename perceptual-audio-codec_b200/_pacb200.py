@@ -114,10 +114,27 @@ class _StubTable(object):
 
 
 class _Unpickler(pickle.Unpickler):
+    """Restricted unpickler for the two reference fixtures.  They reference exactly three globals (Huffman.HuffmanTable,
+    Huffman.Histogram, collections.deque); anything else in a pickle found in the working directory is refused instead of
+    imported -- a hostile huffmanTables.pickle must not be able to run code in a process that merely creates an Engine."""
+    classes = {}
+
     def find_class(self, module, name):
-        if module == "Huffman":
-            return _StubTable
-        return pickle.Unpickler.find_class(self, module, name)
+        if module == "Huffman" and name in ("HuffmanTable", "Histogram", "HuffmanNode"):
+            return self.classes.get(name, _StubTable)
+        if (module, name) == ("collections", "deque"):
+            import collections
+            return collections.deque
+        raise pickle.UnpicklingError("refusing to unpickle %s.%s: the codec's table fixtures only hold Huffman.HuffmanTable, "
+                                     "Huffman.Histogram and collections.deque" % (module, name))
+
+
+def safe_load(handle, classes=None):
+    """pickle.load for huffmanTables.pickle / histograms.pickle with the global whitelist above; `classes` maps the
+    fixture's class names to the caller's classes (the Huffman shim passes its own HuffmanTable / Histogram)."""
+    u = _Unpickler(handle, encoding="latin1")
+    u.classes = classes or {}
+    return u.load()
 
 
 def find_pickle(name="huffmanTables.pickle"):
@@ -220,8 +237,11 @@ class Engine(object):
     KINDS = ("analysis", "scan", "pack", "index", "unpack", "synth")
 
     def set_stream(self, cuda_stream_handle):
-        """use the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None restores the own stream"""
-        self._ck(lib().pac_set_stream(self.ctx, C.c_void_p(cuda_stream_handle or 0)))
+        """use the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream).  Handle 0 is CUDA's legacy default
+        stream (torch's default stream reports 0) and is used as such; None restores the context's own stream
+        (PAC_STREAM_OWN)."""
+        h = C.c_void_p(-1) if cuda_stream_handle is None else C.c_void_p(int(cuda_stream_handle))
+        self._ck(lib().pac_set_stream(self.ctx, h))
 
     def timing(self, on=True):
         self._ck(lib().pac_timing_enable(self.ctx, 1 if on else 0))

@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(32 * kIdxWarps) k_index(const IndexArgs a) {
         }
         nb++;
     }
+    // more chunks than the caller's bound allows (a chain of undersized chunks): malformed, not silently truncated
+    if (st == 0 && nb == a.maxBlocks && pos + 4 <= end) {
+        const uint32_t n0 = rd(pos);
+        if (pos + 4 + (int64_t)n0 + 4 <= end) st = PAC_E_FORMAT;
+    }
     if (lane == 0) { a.nBlocks[s] = nb; a.status[s] = st; }
 }
 

@@ -157,7 +157,11 @@ extern "C" int pac_set_stream(PacCtx *ctx, void *stream) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     timing_flush(ctx);
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->ownStream;
+    // NULL is CUDA's legacy default stream (what torch.cuda.current_stream().cuda_stream reports for torch's default
+    // stream): cudaStreamLegacy names it explicitly, so the internal non-blocking streams are fenced against it by events
+    // like against any other caller stream.  The context's private stream has its own sentinel.
+    if (stream == PAC_STREAM_OWN) ctx->stream = ctx->ownStream;
+    else ctx->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
     return PAC_OK;
 }
 
@@ -504,9 +508,11 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
     if (precision != PAC_PRECISION_FP64 && precision != PAC_PRECISION_FP32) FAIL(PAC_E_ARG, "precision must be 0 (fp64) or 1 (fp32)");
     if (params->nChannels != 2) FAIL(PAC_E_ARG, "only 2 channels are supported (as in the reference, codec.py:46-47)");
     if (params->nMDCTLines != 1024 && params->nMDCTLines != 512) FAIL(PAC_E_ARG, "nMDCTLines must be 1024 or 512");
-    if (params->nScaleBits < 1 || params->nScaleBits > 4 || params->nMantSizeBits < 1 || params->nMantSizeBits > 4 ||
-        params->nTableIDBits < 4 || params->nTableIDBits > 8)
+    if (params->nScaleBits < 1 || params->nScaleBits > 4 || params->nMantSizeBits < 1 || params->nMantSizeBits > 4)
         FAIL(PAC_E_ARG, "unsupported bit-field widths");
+    // the container does not store nTableIDBits and the reference's reader hard-codes 4 (pacfile.py:189): any other width
+    // would write images that neither this library nor the reference can decode
+    if (params->nTableIDBits != 4) FAIL(PAC_E_ARG, "nTableIDBits must be 4 (the .pac reader hard-codes it, pacfile.py:189)");
     if (params->sampleRate < 8000 || params->sampleRate > 192000) FAIL(PAC_E_ARG, "unsupported sample rate");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(PAC_E_NODEVICE, "no CUDA device: the engine has no CPU fallback");
@@ -685,10 +691,8 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         if (rc) return rc;
         a.band_of_line = tb.band_of_line;
     }
-    // one warp per CTA: while it overlaps k_analysis, a scan CTA can only get on an SM by taking the place of a retiring
-    // analysis CTA (20 K registers); seven 1-warp CTAs fit in that space against one 4-warp CTA (measured 1360 vs 1385 ms/step)
-    constexpr int WARPS = 1;
-    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, WARPS><<<(a.S + WARPS - 1) / WARPS, WARPS * 32, 0, LS(ctx)>>>(a); }
+    // one CTA of kScanWarps warps per stream: warp 0 carries the serial state, all warps share the line phase (scan.cuh)
+    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, kScanWarps><<<a.S, kScanWarps * 32, 0, LS(ctx)>>>(a); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;

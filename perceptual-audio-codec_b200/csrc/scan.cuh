@@ -10,6 +10,8 @@
 
 namespace pac {
 
+constexpr int kScanWarps = 8;     // warps per stream CTA of k_scan (half of them per channel in the line phase)
+
 struct StreamState {
     long long extraBits;     // cp.extraBits
     long long bitDeposit;    // huffman.bitDeposit
@@ -38,162 +40,229 @@ struct ScanArgs {
     BandInfo bands;
 };
 
-// bitalloc.BitAlloc on a warp: lane b < NB owns band b.  Returns this lane's bits; *diff = bitDifference.
+// ------------------------------------------------------------------------------------------------------------------
+// bitalloc.BitAlloc (bitalloc.py:129-184) on a warp: lane b < NB owns band b.
+//
+// The reference hands out one bit per iteration (~100-150 iterations per channel, each a pair of 25-way maxima): that
+// loop WAS the serial heart of the reservoir chain.  Its greedy arg-max over SMR_b - 6*bits_b is a merge of 25 strictly
+// decreasing sequences, so as long as nothing happens the state after every entry with key >= tau has been served is
+// known in closed form (bits_b = number of band b's keys >= tau).  warp_bitalloc_jump advances by such cuts and only
+// walks single iterations through the +-0.5 dB zones around the stop thresholds, where the outcome depends on rounding:
+//   * budget: tau is raised by bisection on the EXACT cost until the whole cut is affordable;
+//   * max-NMR stop rule (:163-168): per jump a band class (M/S, L/R) is NORMAL (the rule provably does not fire) or
+//     TERMINAL (it provably fires: the band takes one more bit -- allocate-after-invalidate -- and leaves);
+//   * a band wider than the remaining budget can only ever be invalidated (the budget never grows in the loop): dropped.
+// tests/model_bitalloc.py is the numpy statement of exactly this control flow; tests/test_model.py proves it equal to the
+// plain loop on random and adversarial problems (ties on the 6 dB lattice, thresholds hit exactly, reservoirs from
+// negative to 500 k bits) in both arithmetics.  Typical: 2-3 jumps + 3-4 single iterations per channel.
+//
+// T = double: the reference's arithmetic (fp64 verification mode, bit-exact).  T = float: the fast mode's keys
+// (key = fma(bits, -6, SMR), NMR = key + 6).
+// ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned sortable32(float v) {
     const unsigned u = __float_as_uint(v);
     return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);      // negative: ~u, else u | sign bit (two instructions)
 }
+__device__ __forceinline__ float unsortable32(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// warp maximum; lanes with on == false do not take part; -inf when nobody does
+__device__ __forceinline__ float wmax_on(float v, bool on) {
+    const unsigned k = __reduce_max_sync(0xffffffffu, on ? sortable32(v) : 0u);
+    return k ? unsortable32(k) : -INFINITY;
+}
+__device__ __forceinline__ double wmax_on(double v, bool on) {
+    const unsigned long long key = on ? sortable(v) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+    if (mk == 0ull) return -INFINITY;
+    return __longlong_as_double((long long)((mk >> 63) ? (mk & 0x7fffffffffffffffull) : ~mk));
+}
+__device__ __forceinline__ float ba_key(float smr, int bits) { return fmaf((float)bits, -6.f, smr); }
+__device__ __forceinline__ double ba_key(double smr, int bits) { return smr - bits * 6.; }
+__device__ __forceinline__ float ba_nmr(float smr, int bits) { return ba_key(smr, bits) + 6.f; }          // fast mode: key + 6
+__device__ __forceinline__ double ba_nmr(double smr, int bits) { return smr - (bits - 1) * 6.; }         // bitalloc.py:165
 
-// fp32 fast mode: the SMRs are floats, so the arg-max keys are formed in float (one REDUX per maximum instead of two).
-// The loop is the serial heart of the scan kernel (about 100 iterations per channel), so it carries its state in the form
-// the next iteration needs: per lane the sortable key of SMR - 6*bits (0 once the band is invalid, so "no valid band
-// left" is simply a zero maximum) and of SMR - 6*(bits-1); only the winning lane's keys change per iteration.  Line
-// counts come from a shuffle of the per-lane count, the bit budget is a 32-bit integer (callers fall back to the generic
-// version for budgets that do not fit).
-__device__ __forceinline__ int warp_bitalloc32(int totalBits0, long long extraBits, int maxMantBits, int NB, float smrLane,
-                                               uint32_t lrms, int nLinesLane, long long *diff) {
+// largest n in [lo, cap] with key(j) >= tau for all lo <= j < n: closed-form guess, fixed up with the loop's own key expression
+template <typename T>
+__device__ __forceinline__ int ba_count_ge(T smr, T tau, int lo, int cap) {
+    T g = floor((smr - tau) * (T)(1.0 / 6.0));
+    g = g < (T)-1 ? (T)-1 : (g > (T)64 ? (T)64 : g);          // also maps tau = -inf (g = +inf) to "everything"
+    int n = (int)g + 1;
+    n = n < lo ? lo : n;
+    n = n > cap ? cap : n;
+    while (n > lo && ba_key(smr, n - 1) < tau) n--;
+    while (n < cap && ba_key(smr, n) >= tau) n++;
+    return n;
+}
+
+template <typename T>
+__device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long extraBits, int maxMantBits, int NB, T smrLane,
+                                                  uint32_t lrms, int nLinesLane, long long *diff) {
     const int lane = threadIdx.x & 31;
     const bool inband = lane < NB;
+    const bool isMS = (lrms >> lane) & 1u;
+    const T NINF = (T)-INFINITY;
     int bits = 0;
-    float fbits = 0.f;
-    int totalBits = totalBits0;
-    const unsigned kMS = sortable32(-5.0f), kLR = sortable32(-15.0f);
-    unsigned vkey = inband ? sortable32(smrLane) : 0u;                     // valid bands only
-    unsigned k2 = inband ? sortable32(smrLane + 6.f) : 0u;                 // all bands: SMR - 6*(bits-1)
+    bool valid = inband;
+    long long total = total0;                                              // int(bitBudget + extraBits), :159
     for (;;) {
-        const unsigned mk1 = __reduce_max_sync(0xffffffffu, vkey);
-        if (mk1 == 0u) break;                                              // no valid band left (bitalloc.py:161)
-        const int iMax = __ffs(__ballot_sync(0xffffffffu, vkey == mk1)) - 1;       // first index wins (np.argmax)
-        const unsigned mk2 = __reduce_max_sync(0xffffffffu, k2);
-        const bool below = mk2 < (((lrms >> iMax) & 1u) ? kMS : kLR);      // :165-175
+        valid = valid && (long long)nLinesLane <= total;                   // prune
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (!vmask) break;                                                 // :161
+        const T kcur = ba_key(smrLane, bits);
+        const T m = wmax_on(kcur, valid);                                  // the next pick's key
+        const T F = wmax_on(ba_nmr(smrLane, bits), inband && !valid);      // max NMR held by bands that have left
+        // ---- classify the two band classes for an event-free advance
+        const unsigned msMask = vmask & lrms, lrMask = vmask & ~lrms;
+        T flo = NINF;
+        bool termMS = false, termLR = false, ok = true;
+        if (msMask) {
+            if (m >= (T)-10.5) flo = (T)-10.5;
+            else if (m < (T)-11.5 && F < (T)-5.5) termMS = true;
+            else ok = false;
+        }
+        if (ok && lrMask) {
+            const T k1 = termMS ? wmax_on(kcur, valid && isMS) : NINF;     // first M/S band to leave in this jump
+            const T FB = F > k1 ? F : k1;
+            if (FB >= (T)-14.5) {}                                         // a band that has left keeps max NMR >= -15: L/R rule silent
+            else if (m >= (T)-20.5) flo = flo > (T)-20.5 ? flo : (T)-20.5;
+            else if (m < (T)-21.5 && FB < (T)-15.5) termLR = true;
+            else ok = false;
+        }
+        if (ok && flo < m) {
+            const bool term = isMS ? termMS : termLR;
+            int cap = valid ? (term ? bits + 1 : maxMantBits) : bits;
+            cap = cap > maxMantBits ? maxMantBits : cap;
+            int nb = ba_count_ge<T>(smrLane, flo, bits, cap);
+            int cost = __reduce_add_sync(0xffffffffu, (nb - bits) * nLinesLane);
+            if ((long long)cost > total) {
+                T hi = m + (T)1;                                           // nothing is >= hi
+                T lo = flo;
+                if (flo == NINF) lo = -wmax_on(-ba_key(smrLane, maxMantBits - 1), valid) - (T)1;
+                nb = bits; cost = 0;
+                for (int it = 0; it < 14; it++) {
+                    const T mid = (lo + hi) * (T)0.5;
+                    const int n2 = ba_count_ge<T>(smrLane, mid, bits, cap);
+                    const int c2 = __reduce_add_sync(0xffffffffu, (n2 - bits) * nLinesLane);
+                    if ((long long)c2 <= total) { hi = mid; nb = n2; cost = c2; }
+                    else lo = mid;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, nb != bits)) {
+                total -= cost;
+                if (nb >= maxMantBits || (term && nb > bits)) valid = false;
+                bits = nb;
+                continue;
+            }
+        }
+        // ---- one exact iteration (:162-176)
+        const int iMax = __ffs(__ballot_sync(0xffffffffu, valid && kcur == m)) - 1;   // first index wins (np.argmax)
+        const T mv = wmax_on(ba_nmr(smrLane, bits), valid);
+        const T mxAll = F > mv ? F : mv;                                               // max over ALL bands (:165)
+        const bool below = mxAll < (((lrms >> iMax) & 1u) ? (T)-5 : (T)-15);
         const int nl = __shfl_sync(0xffffffffu, nLinesLane, iMax);
-        const bool afford = totalBits >= nl;                               // :176
-        if (afford) totalBits -= nl;
+        const bool afford = total >= (long long)nl;                                    // :172
+        if (afford) total -= nl;
         if (lane == iMax) {
-            bool valid = !below && afford;                                 // invalidated bands still get this iteration's bit (:176-178)
-            if (afford) { bits += 1; fbits += 1.f; if (bits >= maxMantBits) valid = false; }
-            const float v = fmaf(fbits, -6.f, smrLane);
-            vkey = valid ? sortable32(v) : 0u;
-            k2 = sortable32(v + 6.f);
+            if (below) valid = false;                                                  // still takes this iteration's bit
+            if (afford) { bits += 1; if (bits >= maxMantBits) valid = false; }
+            else valid = false;
         }
     }
     unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);       // bits == 1 -> 0 with refund (:179-180)
-    long long tb = totalBits;
-    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; tb += __shfl_sync(0xffffffffu, nLinesLane, bnd); }
+    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; total += __shfl_sync(0xffffffffu, nLinesLane, bnd); }
     if (bits == 1) bits = 0;
-    *diff = tb - extraBits;
+    *diff = total - extraBits;
     return bits;
 }
 
-__device__ __forceinline__ int warp_bitalloc(double bitBudget, long long extraBits, int maxMantBits, int NB,
-                                             int nLinesLane, double smrLane, uint32_t lrms, const BandInfo &bands,
-                                             long long *diff) {
-    const int lane = threadIdx.x & 31;
-    const bool inband = lane < NB;
-    int bits = 0;
-    bool valid = inband;
-    long long totalBits = (long long)(bitBudget + (double)extraBits);     // int() truncation, bitalloc.py:159
-    while (__ballot_sync(0xffffffffu, valid) != 0u) {
-        // argmax over valid bands of SMR - 6*bits, first index wins (np.argmax)
-        double v = smrLane - bits * 6.;
-        unsigned long long key = inband ? sortable(v) : 0ull;
-        unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-        unsigned hv = valid ? hi : 0u;
-        unsigned mh = __reduce_max_sync(0xffffffffu, hv);
-        bool c1 = valid && hi == mh;
-        unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
-        unsigned win = __ballot_sync(0xffffffffu, c1 && lo == ml);
-        int iMax = __ffs(win) - 1;
-        // max over ALL bands of SMR - 6*(bits-1)   (bitalloc.py:165-168)
-        double v2 = smrLane - (bits - 1) * 6.;
-        unsigned long long k2 = inband ? sortable(v2) : 0ull;
-        unsigned h2 = (unsigned)(k2 >> 32), l2 = (unsigned)k2;
-        unsigned mh2 = __reduce_max_sync(0xffffffffu, h2);
-        unsigned ml2 = __reduce_max_sync(0xffffffffu, (inband && h2 == mh2) ? l2 : 0u);
-        unsigned long long mk = ((unsigned long long)mh2 << 32) | ml2;
-        const unsigned long long kMS = sortable(-5.0), kLR = sortable(-15.0);
-        bool below = ((lrms >> iMax) & 1u) ? (mk < kMS) : (mk < kLR);
-        int nl = bands.lo[iMax + 1] - bands.lo[iMax];
-        bool me = lane == iMax;
-        if (below && me) valid = false;
-        if (totalBits - nl >= 0) {
-            totalBits -= nl;
-            if (me) { bits += 1; if (bits >= maxMantBits) valid = false; }
-        } else if (me) valid = false;
-    }
-    // bits == 1 -> 0 with refund (bitalloc.py:179-180)
-    unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);
-    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; totalBits += bands.lo[bnd + 1] - bands.lo[bnd]; }
-    if (bits == 1) bits = 0;
-    *diff = totalBits - extraBits;
-    (void)nLinesLane;
-    return bits;
-}
-
+// One CTA per stream, WARPS warps (even).  Warp 0 carries the stream's serial state (reservoir, savings pool, byte
+// offset) and runs the two BitAllocs of a block; then ALL warps share the line phase (half of the warps per channel, each
+// a contiguous range of lines: quantise, look up the ten code lengths), whose loads were issued before the BitAllocs so
+// that their latency hides behind them; warp 0 finally picks the table and updates the state.  Two CTA barriers per block.
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_scan(const ScanArgs<T> a) {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    static_assert(WARPS >= 2 && WARPS % 2 == 0, "half of the warps per channel");
+    constexpr int WPC = WARPS / 2;               // warps per channel
+    constexpr int LPLMAX = 1024 / (32 * WPC);    // lines per lane at M = 1024
+    __shared__ unsigned short sBitsSf[2][kMaxBands];      // bits | sf << 8 per (channel, band) of the current block
+    __shared__ unsigned sTot[WARPS][kNTables];            // per-warp totals of the ten table lengths
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x;
     if (s >= a.S) return;
     const int NB = a.bands.nBands, M = a.M;
     const EncConsts &ec = a.ec;
     const int largestScale = (1 << ec.nScaleBits) - 1;
     int nblkStream = a.b0 + a.nb;
     if (a.nSamples) nblkStream = (int)((a.nSamples[s] + M - 1) / M + 1);
-    long long extraBits = a.state[s].extraBits, bitDeposit = a.state[s].bitDeposit, outOff = a.state[s].outOffset;
+    long long extraBits = 0, bitDeposit = 0, outOff = 0;
+    if (warp == 0) { extraBits = a.state[s].extraBits; bitDeposit = a.state[s].bitDeposit; outOff = a.state[s].outOffset; }
     const int nLinesLane = lane < NB ? a.bands.lo[lane + 1] - a.bands.lo[lane] : 0;
     const int bEnd = min(a.b0 + a.nb, nblkStream);
-    constexpr int LPL = 32;                      // lines per lane (M = 1024); M = 512 uses the first 16
-    unsigned bandsPacked[LPL / 4];
+    // line phase geometry: this warp owns lines [l0, l0 + LPW) of channel myCh; lane l owns l0 + 32*j + l
+    const int myCh = warp / WPC, LPW = M / WPC, l0 = (warp % WPC) * LPW, lpl = LPW / 32;
+    unsigned bandsPacked[(LPLMAX + 3) / 4];
 #pragma unroll
-    for (int q = 0; q < LPL / 4; q++) {
+    for (int q = 0; q < (LPLMAX + 3) / 4; q++) {
         unsigned v = 0;
 #pragma unroll
-        for (int r = 0; r < 4; r++) { int i = (4 * q + r) * 32 + lane; v |= (unsigned)(i < M ? a.band_of_line[i] : 0) << (8 * r); }
+        for (int r = 0; r < 4; r++) { const int j = 4 * q + r; v |= (unsigned)(j < lpl ? a.band_of_line[l0 + j * 32 + lane] : 0) << (8 * r); }
         bandsPacked[q] = v;
     }
-    const int lplRun = M / 32;
 
     for (int b = a.b0; b < bEnd; b++) {
         const int64_t w = (int64_t)s * a.nb + (b - a.b0);
-        const uint32_t lrms = a.lrms[w];
-        // withdrawBits, Huffman.py:363-371 (floor division of a positive int)
+        // every warp: its lines of this block (they do not depend on the allocation)
+        T xv[LPLMAX];
         {
-            long long extra = 0;
-            if (bitDeposit > 10) { extra = bitDeposit / 100; bitDeposit -= extra; }
-            else if (bitDeposit < 0) { extra = bitDeposit; bitDeposit = 0; }
-            extraBits += extra;                                            // codec.py:229
+            const T *x = a.lines + (w * 2 + myCh) * M + l0 + lane;
+#pragma unroll
+            for (int j = 0; j < LPLMAX; j++) xv[j] = j < lpl ? x[j * 32] : (T)0;
         }
-        for (int ch = 0; ch < 2; ch++) {
-            const int64_t wc = w * 2 + ch;
-            double smrLane = lane < NB ? (double)a.smr[wc * kMaxBands + lane] : 0.0;
-            double bmaxLane = lane < NB ? (double)a.bmax[wc * kMaxBands + lane] : 0.0;
-            long long diff;
-            int bits;
-            const long long total0 = (long long)(ec.bitBudget + (double)extraBits);          // int() truncation, bitalloc.py:159
-            if (sizeof(T) == 4 && total0 > -(1ll << 30) && total0 < (1ll << 30))
-                bits = warp_bitalloc32((int)total0, extraBits, ec.maxMantBits, NB, (float)smrLane, lrms, nLinesLane, &diff);
-            else bits = warp_bitalloc(ec.bitBudget, extraBits, ec.maxMantBits, NB, nLinesLane, smrLane, lrms, a.bands, &diff);
-            extraBits += diff;                                             // codec.py:260
-            int sfl = scale_factor(bmaxLane, ec.nScaleBits, bits);       // codec.py:274
-            if (lane < NB) { a.ba[wc * kMaxBands + lane] = (uint8_t)bits; a.sf[wc * kMaxBands + lane] = (uint8_t)sfl; }
-            // code lengths under the 10 tables.  Lane l owns lines 32*j + l; per line one 32-byte LUT entry gives all ten
-            // lengths in 12-bit packed slots (a lane's 32 lines cannot overflow a slot), escapes add bitAlloc raw bits
-            // (Huffman.py:292-298).  The 16 lines of a chunk are independent, so their loads overlap.
-            const T *x = a.lines + wc * M;
+        if (warp == 0) {
+            const uint32_t lrms = a.lrms[w];
+            T smrL[2], bmaxL[2];
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                smrL[ch] = lane < NB ? a.smr[(w * 2 + ch) * kMaxBands + lane] : (T)0;
+                bmaxL[ch] = lane < NB ? a.bmax[(w * 2 + ch) * kMaxBands + lane] : (T)0;
+            }
+            // withdrawBits, Huffman.py:363-371 (floor division of a positive int)
+            {
+                long long extra = 0;
+                if (bitDeposit > 10) { extra = bitDeposit / 100; bitDeposit -= extra; }
+                else if (bitDeposit < 0) { extra = bitDeposit; bitDeposit = 0; }
+                extraBits += extra;                                            // codec.py:229
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                const int64_t wc = w * 2 + ch;
+                long long diff;
+                const long long total0 = (long long)(ec.bitBudget + (double)extraBits);          // int() truncation, bitalloc.py:159
+                const int bits = warp_bitalloc_jump<T>(total0, extraBits, ec.maxMantBits, NB, smrL[ch], lrms, nLinesLane, &diff);
+                extraBits += diff;                                             // codec.py:260
+                const int sfl = scale_factor((double)bmaxL[ch], ec.nScaleBits, bits);           // codec.py:274
+                if (lane < NB) {
+                    a.ba[wc * kMaxBands + lane] = (uint8_t)bits; a.sf[wc * kMaxBands + lane] = (uint8_t)sfl;
+                    sBitsSf[ch][lane] = (unsigned short)(bits | (sfl << 8));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- line phase: code lengths under the 10 tables.  Per line one 32-byte LUT entry gives all ten lengths in 12-bit
+        // packed slots (a lane's <= 32 lines cannot overflow a slot), escapes add bitAlloc raw bits (Huffman.py:292-298).
+        {
             unsigned long long acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int j0 = 0; j0 < LPL; j0 += 16) {
-                if (j0 >= lplRun) break;
-                T xv[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) xv[j] = x[(j0 + j) * 32 + lane];
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int bd = (bandsPacked[(j0 + j) >> 2] >> (8 * ((j0 + j) & 3))) & 0xff;
-                    const int bab = __shfl_sync(0xffffffffu, bits, bd);
-                    const int sfb = __shfl_sync(0xffffffffu, sfl, bd);
+            for (int j = 0; j < LPLMAX; j++) {
+                if (j < lpl) {
+                    const int bd = (bandsPacked[j >> 2] >> (8 * (j & 3))) & 0xff;
+                    const unsigned bs = sBitsSf[myCh][bd];
+                    const int bab = (int)(bs & 0xffu), sfb = (int)(bs >> 8);
                     if (bab > 0) {
                         unsigned mag = mant_mag(fabs((double)xv[j]), sfb, largestScale, bab);
                         const ulonglong2 *ep = reinterpret_cast<const ulonglong2 *>(a.lenLut4 + (mag < (unsigned)kLenLutSize ? mag : (unsigned)kLenLutSize));
@@ -203,35 +272,47 @@ k_scan(const ScanArgs<T> a) {
                     }
                 }
             }
-            unsigned tot[kNTables];
 #pragma unroll
-            for (int t = 0; t < 5; t++) { tot[t] = (unsigned)(acc0 >> (12 * t)) & 0xfffu; tot[5 + t] = (unsigned)(acc1 >> (12 * t)) & 0xfffu; }
-            int nMant = 0, origin = 0;
-            {
-                int nm = (lane < NB && bits > 0) ? nLinesLane : 0;
-                nMant = __reduce_add_sync(0xffffffffu, nm);
-                origin = __reduce_add_sync(0xffffffffu, nm * bits);
+            for (int t = 0; t < 5; t++) {
+                const unsigned v0 = __reduce_add_sync(0xffffffffu, (unsigned)(acc0 >> (12 * t)) & 0xfffu);
+                const unsigned v1 = __reduce_add_sync(0xffffffffu, (unsigned)(acc1 >> (12 * t)) & 0xfffu);
+                if (lane == 0) { sTot[warp][t] = v0; sTot[warp][5 + t] = v1; }
             }
-            unsigned best = 0;
-            int bestID = 1;
-#pragma unroll
-            for (int t = 0; t < kNTables; t++) {
-                unsigned v = __reduce_add_sync(0xffffffffu, tot[t]);
-                if (t == 0 || v < best) { best = v; bestID = t + 1; }      // Huffman.py:300-307
-            }
-            bitDeposit += (long long)origin - ((long long)best + nMant + ec.nTableIDBits);   // codec.py:118-120
-            long long nbits = (long long)ec.fixedBits + nMant + best;       // pacfile.py:291-312
-            unsigned nby = (unsigned)((nbits + 7) / 8);                     // :315-316
-            if (lane == 0) {
-                a.tableID[wc] = (uint8_t)bestID;
-                a.nbytes[wc] = nby;
-                a.chunkOff[wc] = outOff;
-            }
-            outOff += 4 + (long long)nby;
         }
-        if (lane == 0 && a.trExtra) { a.trExtra[w] = extraBits; a.trDeposit[w] = bitDeposit; }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                const int64_t wc = w * 2 + ch;
+                const unsigned bs = lane < NB ? sBitsSf[ch][lane] : 0u;
+                const int bits = (int)(bs & 0xffu);
+                const int nm = bits > 0 ? nLinesLane : 0;
+                const int nMant = __reduce_add_sync(0xffffffffu, nm);
+                const int origin = __reduce_add_sync(0xffffffffu, nm * bits);
+                // lane t < 10: total length under table t+1; strictly shortest wins, ties -> lowest ID (Huffman.py:300-307)
+                unsigned tot = 0xffffffu;
+                if (lane < kNTables) {
+                    tot = 0;
+#pragma unroll
+                    for (int q = 0; q < WPC; q++) tot += sTot[ch * WPC + q][lane];
+                }
+                const unsigned bk = __reduce_min_sync(0xffffffffu, (tot << 4) | (unsigned)lane);
+                const unsigned best = bk >> 4;
+                const int bestID = (int)(bk & 15u) + 1;
+                bitDeposit += (long long)origin - ((long long)best + nMant + ec.nTableIDBits);   // codec.py:118-120
+                const long long nbits = (long long)ec.fixedBits + nMant + best;                   // pacfile.py:291-312
+                const unsigned nby = (unsigned)((nbits + 7) / 8);                                 // :315-316
+                if (lane == 0) {
+                    a.tableID[wc] = (uint8_t)bestID;
+                    a.nbytes[wc] = nby;
+                    a.chunkOff[wc] = outOff;
+                }
+                outOff += 4 + (long long)nby;
+            }
+            if (lane == 0 && a.trExtra) { a.trExtra[w] = extraBits; a.trDeposit[w] = bitDeposit; }
+        }
     }
-    if (lane == 0) {
+    if (warp == 0 && lane == 0) {
         a.state[s].extraBits = extraBits;
         a.state[s].bitDeposit = bitDeposit;
         a.state[s].outOffset = outOff;

@@ -85,7 +85,9 @@ __global__ void k_bitalloc(int n, const double *bitBudget, const long long *extr
     const int NB = bands.nBands;
     double s = lane < NB ? smr[(int64_t)p * NB + lane] : 0.0;
     long long d;
-    int b = warp_bitalloc(bitBudget[p], extraBits[p], maxMantBits, NB, 0, s, lrms[p], bands, &d);
+    const int nl = lane < NB ? bands.lo[lane + 1] - bands.lo[lane] : 0;
+    const long long total0 = (long long)(bitBudget[p] + (double)extraBits[p]);               // int() truncation, bitalloc.py:159
+    int b = warp_bitalloc_jump<double>(total0, extraBits[p], maxMantBits, NB, s, lrms[p], nl, &d);
     if (lane < NB) bits[(int64_t)p * NB + lane] = b;
     if (lane == 0) diff[p] = d;
 }

@@ -146,6 +146,53 @@ def test_shim_bitalloc(kats, oracle, pb):
         assert list(b1[0]) == list(b2) and int(d1[0]) == d2, i
 
 
+def bitalloc_problems(rng, n):
+    """random + adversarial BitAlloc inputs covering every regime of the kernel's event-driven water-filling (scan.cuh:
+    warp_bitalloc_jump): budget-limited, reservoir-rich, mixed M/S + L/R, SMRs on the 6 dB lattice (ties across bands) and
+    on the stop thresholds, bands that max out with NMR above the thresholds, empty (-96) bands, negative reservoirs."""
+    out = []
+    for t in range(n):
+        kind = t % 13
+        smr = rng.uniform(-60, 50, 25)
+        if kind == 1:
+            smr[:] = smr[0]
+        elif kind == 2:
+            smr = np.round(smr / 6) * 6 + rng.choice([0, 0, 0, 1e-9, -1e-9], 25)
+        elif kind == 3:
+            smr[rng.integers(0, 25, 3)] = -96.0
+        elif kind == 4:
+            smr = rng.uniform(-30, -5, 25)
+        elif kind == 5:
+            smr = np.round(rng.uniform(-30, 10, 25) * 2) / 2
+        elif kind == 6:
+            smr = rng.uniform(60, 110, 25)
+        elif kind == 7:
+            smr = rng.uniform(-25, -9, 25)
+        elif kind == 8:
+            smr = rng.choice([-11., -5., -17., -21., -15., -10.5, -11.5, -20.5, -21.5], 25)
+        lrms = rng.integers(0, 2, 25)
+        if kind == 9:
+            lrms[:] = 0
+        elif kind == 10:
+            lrms[:] = 1
+        extra = int(rng.choice([rng.integers(-4000, 4000), rng.integers(0, 200), rng.integers(3000, 500000), 0]))
+        budget = float(rng.choice([2116.48, 1382.0, 5840.3, 300.5]))
+        out.append((budget, extra, smr, lrms))
+    return out
+
+
+def test_bitalloc_jump_regimes_vs_oracle(oracle, pb):
+    """pac_bitalloc (the same warp routine k_scan runs) on 4000 problems in one launch == the oracle's plain loop (bitalloc.py:129-184)."""
+    e = pb.engine()
+    probs = bitalloc_problems(np.random.default_rng(2024), 4000)
+    bb = np.array([p[0] for p in probs]); eb = np.array([p[1] for p in probs], np.int64)
+    smr = np.stack([p[2] for p in probs]); masks = np.array([sum(int(v) << b for b, v in enumerate(p[3])) for p in probs], np.int32)
+    bits, diff = e.bitalloc(bb, eb, 16, smr, masks)
+    for i, (budget, extra, s, lr) in enumerate(probs):
+        b2, d2 = oracle.bitalloc(budget, extra, 16, 25, NL44, s, [int(v) for v in lr])
+        assert list(bits[i]) == list(b2) and int(diff[i]) == d2, (i, i % 13, budget, extra)
+
+
 def test_shim_bitalloc_alt(kats, oracle, pb):
     """bitalloc.py:22-125 through pac_bitalloc_alt: the reference's own answers, random problems vs the oracle, and the
     inputs for which the reference never returns."""
@@ -280,24 +327,49 @@ def test_analysis_fp64_vs_reference_dumps(e64, stages):
         np.testing.assert_allclose(r["smr"][i], stages[k + ".smr"], rtol=0, atol=1e-9, err_msg=k)
 
 
+def line_tolerance(ref_lines, lrms_mask, ref_mdct=None):
+    """Tolerance of the fp32 fast mode's MDCT lines, per line, against the reference's float64 values.
+      * 1e-5 * |ref|  -- north_star's "within 1e-5 relative";
+      * + 1e-11 * max|ref| of the block: the REFERENCE's own rounding noise.  Its MDCT is a 2048-point complex FFT (mdct.py:62-71)
+        whose float64 round-off sits at ~1.5e-13 of the block's largest line on every line (measured against long double, DESIGN.md);
+        the kernel's fold + 512-point FFT in fp64 is more accurate than that, so lines 1e-7 and more below the block's maximum cannot
+        agree to 1e-5 relative with ANY exact implementation.  (Round 1 used 1e-7 here, the resolution an fp32 FFT would need; the
+        kernel computes the MDCT in fp64 and rounds once, so that floor was 10 000 times wider than necessary.)
+      * + 1.2e-7 * max(|L|, |R|) at that line, in M/S bands only: the selected lines there are (L +- R)/2 formed from the fp32-rounded
+        L and R (psychoac.py:551 in float), so a side line much smaller than L and R inherits their fp32 rounding (2 * 2^-24).
+    Returns the per-line tolerance array for lines [2][M] of one block."""
+    M = ref_lines.shape[-1]
+    tol = 1e-5 * np.abs(ref_lines) + 1e-11 * np.max(np.abs(ref_lines))
+    band = np.repeat(np.arange(len(NL44)), NL44)[:M]
+    ms = ((int(lrms_mask) >> band) & 1).astype(bool)
+    big = np.maximum(np.abs(ref_lines[0] + ref_lines[1]), np.abs(ref_lines[0] - ref_lines[1]))   # |L|, |R| from (M, S)
+    tol = tol + 1.2e-7 * np.where(ms, big, 0.0)[None, :]
+    return tol
+
+
 def test_analysis_fp32_within_1e5_of_reference(e32, stages):
     """north_star: fp32 fast mode MDCT/SMR within 1e-5 relative of the reference.
-    Tolerances used: every MDCT line |d| <= 1e-5 * |ref| + 1e-7 * max|ref| (per-line relative, with a floor at the
-    fp32 resolution of the block's largest line); every SMR value |d| <= 1e-5 * max(|ref|, 10) dB -- SMR is a
-    difference of two ~50..90 dB quantities, so "relative" is taken against 10 dB when |SMR| is smaller."""
+    Raw MDCT lines (the L/R transform itself): |d| <= 1e-5 * |ref| + 1e-11 * max|ref| on every line.  LRMS-selected lines: the
+    same, plus the fp32 resolution of L and R at that line in M/S bands (line_tolerance).  Every SMR value
+    |d| <= 1e-5 * max(|ref|, 10) dB -- SMR is a difference of two ~50..90 dB quantities, so "relative" is taken against 10 dB
+    when |SMR| is smaller."""
     keys, data = _stage_inputs(stages)
     r = e32.analysis(data)
-    worst_l = worst_s = 0.0
+    worst_m = worst_l = worst_s = 0.0
     for i, k in enumerate(keys):
-        assert int(r["lrms"][i]) == sum(int(v) << b for b, v in enumerate(stages[k + ".lrms"])), k
+        mask = sum(int(v) << b for b, v in enumerate(stages[k + ".lrms"]))
+        assert int(r["lrms"][i]) == mask, k
         assert list(r["oscale"][i]) == list(stages[k + ".oscale"]), k
+        rm = stages[k + ".mdct"]
+        em = np.abs(r["mdct"][i] - rm) / (1e-5 * np.abs(rm) + 1e-11 * np.max(np.abs(rm)))
         ref = stages[k + ".lines"]
-        el = np.abs(r["lines"][i] - ref) / (1e-5 * np.abs(ref) + 1e-7 * np.max(np.abs(ref)))
+        el = np.abs(r["lines"][i] - ref) / np.maximum(line_tolerance(ref, mask), 1e-300)
         rs = stages[k + ".smr"]
         es = np.abs(r["smr"][i] - rs) / (1e-5 * np.maximum(np.abs(rs), 10.0))
-        worst_l, worst_s = max(worst_l, el.max()), max(worst_s, es.max())
-    print("fp32 analysis: worst line error %.3f x tol, worst SMR error %.3f x tol" % (worst_l, worst_s))
-    assert worst_l <= 1.0 and worst_s <= 1.0
+        worst_m, worst_l, worst_s = max(worst_m, em.max()), max(worst_l, el.max()), max(worst_s, es.max())
+    print("fp32 analysis: worst raw MDCT line error %.3f x tol, worst selected-line error %.3f x tol, worst SMR error %.3f x tol"
+          % (worst_m, worst_l, worst_s))
+    assert worst_m <= 1.0 and worst_l <= 1.0 and worst_s <= 1.0
 
 
 def test_analysis_vs_oracle_on_seeded_edge_blocks(e64, oracle):
@@ -358,14 +430,21 @@ def test_full_corpus_fp64_byte_exact(e64, manifest):
         assert tuple(int(v) for v in e64.last_final_state[i]) == (rec["bitDeposit_end"], rec["extraBits_end"]), n
     for n, (pcm, sr, nh) in zip(names, e64.decode_batch(outs)):
         assert sha(pbat.wav_bytes(pcm, sr, nh)) == manifest["files"][n]["out_sha256"], n
-    print("corpus files checked byte-exact (encode + decode): %d" % len(names))
+    print("corpus files checked byte-exact (encode + decode): %d of %d in the manifest" % (len(names), len(manifest["files"])))
+    # BASELINE config 2 is the WHOLE corpus: a run that silently shrank to the two committed fixtures must fail, not pass.
+    # tests/golden/_corpus (git-ignored copies of the reference's inputs/*.wav) is populated by __graft_entry__.build() wherever
+    # /root/reference exists and travels to the GPU box with the snapshot; PAC_ALLOW_PARTIAL_CORPUS=1 is for deliberate partial runs.
+    if os.environ.get("PAC_ALLOW_PARTIAL_CORPUS") != "1":
+        missing = sorted(set(manifest["files"]) - set(names))
+        assert not missing, "corpus incomplete: %d of %d files present (missing %s); run __graft_entry__.build() where /root/reference " \
+                            "exists, or set PAC_ALLOW_PARTIAL_CORPUS=1" % (len(names), len(manifest["files"]), missing[:4])
     assert len(names) >= 2
 
 
 def test_full_corpus_fp32_within_tolerance_of_oracle(e32, oracle):
     """fp32 fast mode on EVERY block of every inputs/*.wav (not only the 16 dumped ones), against the oracle's per-block
     taps, with the tolerance formulas of test_analysis_fp32_within_1e5_of_reference:
-      * every MDCT line of every block (whose M/S decision agrees) within tolerance -- no exceptions;
+      * every MDCT line of every block (whose M/S decision agrees) within line_tolerance -- no exceptions;
       * SMR: within tolerance except where findpeaks (psychoac.py:158-191) flips.  Its strict comparisons
         P[k] > P[k-1], P[k] > P[k+1] between two nearly equal neighbouring bins are decided by rounding noise (1e-16 in the
         reference, 1e-7 in fp32); a flip moves or removes ONE masker and shifts one threshold curve by up to a few dB over
@@ -397,7 +476,8 @@ def test_full_corpus_fp32_within_tolerance_of_oracle(e32, oracle):
         ref = otr["lines"][same]
         got = tr["lines"][i][:nb][same]
         mx = np.max(np.abs(ref), axis=(1, 2), keepdims=True)
-        el = np.abs(got - ref) / (1e-5 * np.abs(ref) + 1e-7 * np.maximum(mx, 1e-300))
+        tolv = np.stack([line_tolerance(ref[j], otr["lrms"][same][j]) for j in range(len(ref))]) if len(ref) else np.zeros_like(ref)
+        el = np.abs(got - ref) / np.maximum(tolv, 1e-300)
         rs = otr["smr"][same]
         es = np.abs(tr["smr"][i][:nb][same] - rs) / (1e-5 * np.maximum(np.abs(rs), 10.0))
         if el.size:
@@ -566,6 +646,33 @@ def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
     assert abs(len(enc) - 102379) <= 0.01 * 102379
 
 
+def test_device_input_produced_on_torchs_default_stream_without_sync(pb, oracle):
+    """pac_set_stream with handle 0 (what torch.cuda.current_stream().cuda_stream reports for torch's default stream) means CUDA's
+    legacy default stream, not a private one: PCM that torch kernels are still producing when pac_encode_batch is called must be
+    seen complete, with no torch.cuda.synchronize() in between (the library used to map 0 to its own non-blocking
+    stream and raced with the producer)."""
+    import torch
+    e = pb.Engine(0, "fp64")
+    assert torch.cuda.current_stream().cuda_stream == 0
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    pcm = np.stack([synth_pcm(21, 24 * 1024), synth_pcm(22, 24 * 1024, "mono")])
+    src = torch.from_numpy(pcm).cuda()
+    dst = torch.zeros_like(src)
+    out = torch.zeros(2, e.encode_bound(pcm.shape[1]), dtype=torch.uint8, device="cuda")
+    big = torch.randn(6144, 6144, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(30):                                   # ~100 ms of queued work in front of the producer
+        big = (big @ big) * 1e-4
+    dst.copy_(src)                                        # the "producer": still pending when the library is called
+    _, ob = e.encode_batch(dst, out=out, cap=out.shape[1])
+    host = out.cpu().numpy()
+    for s in range(2):
+        assert host[s, :ob[s]].tobytes() == oracle.encode_stream(pcm[s])[0], s
+    e.set_stream(None)                                    # back on the context's own stream
+    assert e.encode_batch(pcm)[0] == oracle.encode_stream(pcm[0])[0]
+    e.close()
+
+
 def test_output_capacity_error(e64):
     pcm = synth_pcm(1, 20000)
     with pytest.raises(Exception) as ei:
@@ -636,7 +743,30 @@ def test_codec_encode_tuple_structure(gold_dir, oracle):
         mags = [int(v) & ((1 << (int(b) - 1)) - 1) for v, b in zip(m, bits)]
         codes, t2 = h.encodeData(cp, mags, ba[ch])
         assert t2 == tid[ch] and codes == hc[ch]
+        # ... and both equal the strings the reference's pickled table holds for the oracle's mantissas under the oracle's table ID
+        # (escape = escape code + the magnitude in bitAlloc bits, Huffman.py:292-298) -- anchored on the fixture, not on the shim
+        import oracle as omod
+        enc = omod.load_tables()[int(otr["tableID"][61][ch])]
+        want_codes = [enc[mg] if mg in enc else enc[-1] + format(mg, "0%db" % int(b)) for mg, b in zip(mags, bits)]
+        assert hc[ch] == want_codes
     # and Decode of those fields == oracle's decoder on the same chunk
     mant = np.stack([otr["mant"][61, 0], otr["mant"][61, 1]])
     dL, dR = codec.Decode(sf, ba, mant, osc, cp, lrms)
     assert dL.shape == (2048,) and np.isfinite(dL).all() and np.isfinite(dR).all()
+    # ... == codec.Decode restated with the oracle's primitives (codec.py:25-65): vDequantize per band, / 2^overallScale, the M/S
+    # recombination with the reference's aliasing (L' = M - S, R' = L' + S = M), IMDCT, SineWindow
+    lines = np.zeros((2, 1024))
+    lo = np.concatenate([[0], np.cumsum(NL44)])
+    for ch in range(2):
+        for bd in range(25):
+            if ba[ch][bd]:
+                lines[ch, lo[bd]:lo[bd + 1]] = oracle.vdequantize(int(sf[ch][bd]), mant[ch, lo[bd]:lo[bd + 1]].astype(np.int64), 4, int(ba[ch][bd]))
+        lines[ch] /= float(1 << int(osc[ch]))
+    for bd in range(25):
+        if lrms[bd]:
+            sl = slice(lo[bd], lo[bd + 1])
+            lines[0, sl] = lines[0, sl] - lines[1, sl]
+            lines[1, sl] = lines[0, sl] + lines[1, sl]
+    want = [oracle.sine_window(oracle.imdct(lines[ch], 1024, 1024)) for ch in range(2)]
+    for got, w in ((dL, want[0]), (dR, want[1])):
+        assert np.max(np.abs(got - w)) <= 1e-12 * max(np.max(np.abs(w)), 1e-300)

@@ -189,3 +189,23 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_hostile_pickle_in_cwd_is_refused(tmp_path, monkeypatch):
+    """The reference opens huffmanTables.pickle relative to the CWD (Huffman.py:257-260) and so does the engine; a pickle found there
+    that references anything but the fixture's three globals must be refused, not executed."""
+    import pickle
+    import _pacb200
+
+    class Evil(object):
+        def __reduce__(self):
+            return (os.system, ("touch %s" % (tmp_path / "pwned"),))
+
+    (tmp_path / "huffmanTables.pickle").write_bytes(pickle.dumps({1: Evil()}, protocol=0))
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(pickle.UnpicklingError):
+        _pacb200.load_encoding_tables()
+    assert not (tmp_path / "pwned").exists()
+    monkeypatch.chdir(os.path.dirname(_pacb200.__file__))
+    tabs = _pacb200.load_encoding_tables()               # the packaged fixture still loads
+    assert sorted(tabs) == list(range(1, 11))

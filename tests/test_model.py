@@ -171,3 +171,47 @@ def test_incremental_bitalloc_loop_equals_plain_restatement():
             k2[iMax] = _sortable32(f32(v + f32(6)))
         total += nl[bits == 1].sum(); bits[bits == 1] = 0
         assert np.array_equal(bits, want[0]) and total - extra == want[1], trial
+
+
+def test_event_driven_bitalloc_equals_plain_loop():
+    """csrc/scan.cuh: warp_bitalloc_jump (stated in tests/model_bitalloc.py) == the plain one-bit-per-iteration loop of
+    bitalloc.BitAlloc (bitalloc.py:157-184), in the reference's float64 arithmetic and in the fast mode's float32 keys, on random
+    and adversarial problems: 6 dB lattice ties, SMRs sitting on the stop thresholds and on the jump margins, maxed-out bands with
+    NMR above the thresholds, empty bands, all-M/S, all-L/R, budgets from a few hundred bits to a 500 k-bit reservoir."""
+    import model_bitalloc as mb
+    rng = np.random.default_rng(7)
+    it_plain = it_fast = 0
+    for trial in range(1200):
+        T = np.float64 if trial % 2 == 0 else np.float32
+        kind = trial % 13
+        smr = rng.uniform(-60, 50, 25)
+        if kind == 1:
+            smr[:] = smr[0]
+        elif kind == 2:
+            smr = np.round(smr / 6) * 6 + rng.choice([0, 0, 0, 1e-9, -1e-9], 25)
+        elif kind == 3:
+            smr[rng.integers(0, 25, 3)] = -96.0
+        elif kind == 4:
+            smr = rng.uniform(-30, -5, 25)
+        elif kind == 5:
+            smr = np.round(rng.uniform(-30, 10, 25) * 2) / 2
+        elif kind == 6:
+            smr = rng.uniform(60, 110, 25)
+        elif kind == 7:
+            smr = rng.uniform(-25, -9, 25)
+        elif kind == 8:
+            smr = rng.choice([-11., -5., -17., -21., -15., -10.5, -11.5, -20.5, -21.5], 25)
+        lrms = rng.integers(0, 2, 25)
+        if kind == 9:
+            lrms[:] = 0
+        elif kind == 10:
+            lrms[:] = 1
+        extra = int(rng.choice([rng.integers(-4000, 4000), rng.integers(0, 200), rng.integers(3000, 500000), 0]))
+        total0 = int(float(rng.choice([2116.48, 1382.0, 5840.3, 300.5])) + extra)
+        smrT = smr.astype(T)
+        b1, d1, i1 = mb.plain(total0, extra, smrT, lrms, T=T)
+        b2, d2, i2, _ = mb.fast(total0, extra, smrT, lrms, T=T)
+        assert np.array_equal(b1, b2) and d1 == d2, (trial, kind, extra, total0)
+        it_plain += i1; it_fast += i2
+    print("single iterations per problem: plain %.1f, event-driven %.1f" % (it_plain / 1200.0, it_fast / 1200.0))
+    assert it_fast * 5 < it_plain
