@@ -140,9 +140,77 @@ def cpu_baseline_run(pcm_host, seconds_each, cores):
     n = int(seconds_each * FS)
     batch = np.ascontiguousarray(pcm_host[:, :n])
     t0 = time.time()
-    O.encode_batch(batch, nthreads=cores)
+    coded = O.encode_batch(batch, nthreads=cores)
     dt = time.time() - t0
+    cpu_baseline_run.coded = coded
     return batch.shape[0] * seconds_each / dt, dt
+
+
+def parity_leg(pcm_host, seconds_each, cores, device_index):
+    """north_star's two correctness modes, measured on the streams the cpu_baseline leg has just encoded with the oracle and
+    reported in the JSON line: (a) fp64 verification mode: .pac bytes == the oracle's, stream by stream; (b) fp32 fast mode:
+    mismatch rates of the quantities the reference defines (M/S decision codec.py:96-102, overall scale :245, bitAlloc :258,
+    scaleFactor :274, mantissa codes :276-277, tableID Huffman.py:309) and the worst MDCT-line / SMR error in units of 1e-5
+    relative, against the oracle's per-block trace of a sub-sample (the traced oracle is single-threaded per stream)."""
+    import _pacb200
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle as orc
+    O = orc.get()
+    n = int(seconds_each * FS)
+    batch = np.ascontiguousarray(pcm_host[:, :n])
+    want = cpu_baseline_run.coded
+    e64 = _pacb200.Engine(device_index, "fp64")
+    got = e64.encode_batch(batch)
+    e64.close()
+    same = [g == w for g, w in zip(got, want)]
+    out = {"fp64_bytes_equal_oracle": bool(all(same)), "fp64_streams_checked": len(same), "fp64_streams_equal": int(sum(same)),
+           "fp64_bytes_checked": int(sum(len(w) for w in want))}
+    # fp32 fast mode against the traced oracle: the first 4 s of every sampled stream
+    nt = min(n, 4 * FS)
+    sub = np.ascontiguousarray(batch[:, :nt])
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        otr = list(ex.map(lambda s: O.encode_stream(sub[s], trace=True)[1], range(sub.shape[0])))
+    e32 = _pacb200.Engine(device_index, "fp32")
+    _, tr = e32.encode_batch(sub, trace=True)
+    e32.close()
+    cnt = {k: 0 for k in ("lrms", "oscale", "ba", "sf", "tableID", "mant")}
+    mis = dict(cnt)
+    worst_line = worst_smr = 0.0
+    smr_over = smr_n = 0
+    nl = np.array([5, 4, 5, 5, 5, 5, 7, 7, 7, 9, 10, 11, 13, 15, 17, 21, 26, 32, 42, 51, 61, 83, 116, 163, 304])
+    band = np.repeat(np.arange(25), nl)
+    for s, o in enumerate(otr):
+        nb = len(o["lrms"])
+        bits = ((o["lrms"][:, None] >> np.arange(25)[None, :]) & 1)
+        gbits = ((tr["lrms"][s][:nb, None] >> np.arange(25)[None, :]) & 1)
+        mis["lrms"] += int(np.sum(bits != gbits)); cnt["lrms"] += bits.size
+        for k in ("oscale", "ba", "sf", "tableID"):
+            mis[k] += int(np.sum(tr[k][s][:nb] != o[k])); cnt[k] += o[k].size
+        coded = (np.repeat(o["ba"], nl, axis=2) > 0) | (np.repeat(tr["ba"][s][:nb], nl, axis=2) > 0)
+        mis["mant"] += int(np.sum((tr["mant"][s][:nb] != o["mant"]) & coded)); cnt["mant"] += int(np.sum(coded))
+        agree = (tr["lrms"][s][:nb] == o["lrms"]) & np.all(tr["oscale"][s][:nb] == o["oscale"], axis=1)
+        ref, g = o["lines"][agree], tr["lines"][s][:nb][agree]
+        if ref.size:
+            ms = ((o["lrms"][agree][:, None] >> band[None, :]) & 1).astype(bool)
+            big = np.maximum(np.abs(ref[:, 0] + ref[:, 1]), np.abs(ref[:, 0] - ref[:, 1]))
+            # tolerance of tests/test_gpu_parity.py:line_tolerance: 1e-5 relative + the reference's own FFT noise floor (1e-11 of the
+            # block maximum) + the fp32 resolution of L and R at that line in M/S bands
+            tol = 1e-5 * np.abs(ref) + 1e-11 * np.max(np.abs(ref), axis=(1, 2), keepdims=True) + 1.2e-7 * np.where(ms, big, 0.0)[:, None, :]
+            worst_line = max(worst_line, float(np.max(np.abs(g - ref) / np.maximum(tol, 1e-300))))
+            rs, gs = o["smr"][agree], tr["smr"][s][:nb][agree]
+            es = np.abs(gs - rs) / (1e-5 * np.maximum(np.abs(rs), 10.0))
+            smr_over += int(np.sum(es > 1.0)); smr_n += es.size
+            worst_smr = max(worst_smr, float(np.quantile(es, 0.999)))
+    out["fp32"] = {"sample": "%d streams x %.0f s" % (sub.shape[0], nt / FS),
+                   "mismatch_rate": {k: (mis[k] / cnt[k] if cnt[k] else None) for k in cnt},
+                   "compared": cnt,
+                   "worst_line_error_in_units_of_tolerance": worst_line,
+                   "smr_error_p999_in_units_of_1e-5_rel": worst_smr,
+                   "smr_values_over_1e-5_rel": smr_over, "smr_values": smr_n,
+                   "note": "mant = signed mantissa codes of every line coded by either side; SMR values over tolerance are peak-picking flips "
+                           "(findpeaks' strict comparisons between nearly equal bins, psychoac.py:166-168), a discrete mismatch like a flipped M/S decision"}
+    return out
 
 
 def reference_arm(args):
@@ -153,7 +221,10 @@ def reference_arm(args):
         return 0
     import torch
     cores = os.cpu_count() or 1
+    # the corpus is defined by torch's CUDA generator (same seeds -> same streams as the repo arm).  Without a CUDA device the CPU
+    # generator draws DIFFERENT samples of the same signal model for the same seeds: say so in the line instead of staying silent.
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    corpus_note = "" if dev != "cpu" else " [no CUDA device: torch CPU generator, same signal model but not the same samples as the repo arm]"
     sec = args.ref_seconds
     n = int(sec * FS)
     S = cores
@@ -166,7 +237,7 @@ def reference_arm(args):
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
-    sample = "%d streams x %.0f s of the synthetic corpus (stream ids 0..%d), one stream per host thread" % (S, sec, S - 1)
+    sample = "%d streams x %.0f s of the synthetic corpus (stream ids 0..%d), one stream per host thread%s" % (S, sec, S - 1, corpus_note)
     line = {"impl": "reference", "metric": "audio-seconds encoded per second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -195,6 +266,8 @@ def main():
                     help="BASELINE.json configs[4]: also run the bitrate sweep 64..256 kb/s/ch (encode and decode-only, extra 'bitrate_sweep' key)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity leg that rides on the cpu_baseline sample")
+    ap.add_argument("--no-stages", action="store_true", help="skip the MDCT-only stage timing (roofline.stages)")
     ap.add_argument("--decode", action="store_true", help="also time decode-only throughput of the coded corpus (extra 'decode' key)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -270,6 +343,35 @@ def main():
     value = audio_s * args.steps / elapsed
     total_bytes = int(counts.sum().item())
 
+    # ---- stage split of the analysis kernel (SURVEY.md 8d "Which roofline"): the window+MDCT stage by itself (the MDCT-only
+    # instantiation of k_analysis, pac_mdct_batch) and the whole analysis kernel by itself (pac_analysis_batch: not overlapped with
+    # scan/pack as inside the pipeline); SMR stage = the difference.  Device-resident corpus, CUDA-event time of the launches.
+    stages = None
+    if not args.no_stages:
+        eng.mdct_batch(pcm, want=False)
+        ms_m = eng.mdct_batch(pcm, want=False)[2]
+        eng.analysis_batch_ms(pcm)
+        ms_a = eng.analysis_batch_ms(pcm)
+        nb_loc = len(mine) * nblk
+        peak_s, _ = measured_peaks()
+        lb = 4 if args.precision == "fp32" else 8
+        by_m = 4096 + 2 * 1024 * lb + 2                     # PCM in + scaled L/R lines + two overall scales out
+        by_s = 4096 + 2 * 25 * lb + 8                       # a stand-alone SMR stage: PCM in + band SMRs + LRMS/scales out
+        algo_a = ALGO_BYTES_FP32 if args.precision == "fp32" else ALGO_BYTES_FP64
+        gbs = lambda by, ms: by * nb_loc / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages = {"blocks": nb_loc, "rank": rank,
+                  "mdct": {"kernel": "k_analysis<MDCT_ONLY> (PCM->fraction, SineWindow, MDCT, overall scale)", "ms": ms_m,
+                           "ns_per_block": ms_m * 1e6 / nb_loc, "algorithmic_bytes_per_block": by_m, "achieved": gbs(by_m, ms_m),
+                           "frac": gbs(by_m, ms_m) / peak_s},
+                  "analysis_alone": {"kernel": "k_analysis by itself (persistent grid, nothing co-running)", "ms": ms_a,
+                                     "ns_per_block": ms_a * 1e6 / nb_loc, "algorithmic_bytes_per_block": algo_a,
+                                     "achieved": gbs(algo_a, ms_a), "frac": gbs(algo_a, ms_a) / peak_s},
+                  "smr": {"kernel": "analysis_alone - mdct (M/S decision + six threshold curves + band SMR)", "ms": ms_a - ms_m,
+                          "ns_per_block": (ms_a - ms_m) * 1e6 / nb_loc, "algorithmic_bytes_per_block": by_s,
+                          "achieved": gbs(by_s, ms_a - ms_m), "frac": gbs(by_s, ms_a - ms_m) / peak_s,
+                          "share_of_analysis_time": (ms_a - ms_m) / ms_a if ms_a > 0 else None}}
+        log("[rank %d] stages: %s" % (rank, json.dumps(stages)))
+
     # ---- decode-only throughput (BASELINE.json configs[4]): the coded images are decoded where pac_encode_batch left them
     dec = None
     if args.decode:
@@ -296,7 +398,14 @@ def main():
         sd_all = torch.tensor([Sd], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(sd_all)
+        # decode roofline: algorithmic bytes = coded images in + int16 PCM out, over the whole decode call (index + unpack + synth)
+        dbytes = float(np.sum(ob_h)) + float(Sd) * float(ns[0]) * 4.0
+        dgbs = dbytes * args.steps / float(dl.item()) / 1e9
+        dpeak, dsrc = measured_peaks()
         dec = {"value": int(sd_all.item()) * args.seconds * args.steps / float(dl.item()), "unit": "audio-s/s",
+               "roofline": {"bound": "hbm", "rank": rank, "algorithmic_bytes_per_step": dbytes, "achieved": dgbs, "peak": dpeak, "unit": "GB/s",
+                            "frac": dgbs / dpeak, "peak_source": dsrc,
+                            "note": "whole decode call of this rank (k_index + k_unpack + k_synth); bytes = coded images read + PCM written"},
                "ms_per_step": float(dl.item()) / args.steps * 1e3, "streams": int(sd_all.item()), "samples_per_stream": int(ns[0]),
                "input": "coded images left on the device by pac_encode_batch ([S][cap] strided), PCM written to device memory",
                "kernels_ms": {k: v[0] for k, v in tmd.items() if v[1]}}
@@ -383,6 +492,7 @@ def main():
             "frac": ach / peak, "peak_source": peak_src,
             "traffic": (traffic["dram_bytes_per_block"] * blocks_local / max(a_cnt, 1)) if traffic and traffic.get("dram_bytes_per_block") else None,
             "traffic_source": traffic.get("source") if traffic else None,
+            "stages": stages,
             "algorithmic_bytes_per_block": algo, "blocks_per_launch": blocks_local / max(a_cnt, 1),
             "avg_launch_ms": a_ms / max(a_cnt, 1), "launches": a_cnt,
             # the stage is issue-bound, so the same launch is also placed on the SM issue roofline: warp instructions per block
@@ -397,6 +507,7 @@ def main():
                     + ", ".join("%s %.1f ms" % (k, v[0]) for k, v in tm.items() if v[1])}
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:       # the CPU port is timed beside the N=1 run only
         cores = os.cpu_count() or 1
         sec = args.ref_seconds
@@ -405,6 +516,10 @@ def main():
         v, dt = cpu_baseline_run(pcm_s, sec, cores)
         cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": "%d streams x %.0f s of the synthetic corpus, one per host thread, %.1f s wall" % (cores, sec, dt)}
+        if not args.no_parity:
+            t0 = time.time()
+            parity = parity_leg(pcm_s, sec, cores, local)
+            log("parity leg: %.1f s: %s" % (time.time() - t0, json.dumps(parity)))
 
     if rank == 0:
         line = {"metric": "audio-seconds encoded per second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -415,7 +530,7 @@ def main():
                            "streams": S, "seconds_per_stream": args.seconds, "blocks_per_stream": nblk, "targetBitsPerSample": args.tbps,
                            "cache": "inputs (%.1f GB per rank) far larger than the 126 MB L2; no flush needed" % (len(mine) * n * 4 / 1e9),
                            "coded_bytes": total_bytes},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         if dec:
             line["decode"] = dec
         if sweep:

@@ -74,6 +74,7 @@ typedef struct {
     int32_t *nbytes;      /* [S][B][2]        chunk payload bytes                  pacfile.py:291-317 */
     int64_t *extraBits;   /* [S][B]           cp.extraBits after the block         codec.py:229,260 */
     int64_t *bitDeposit;  /* [S][B]           huffman.bitDeposit after the block   codec.py:120 */
+    int32_t *mant;        /* [S][B][2][nMDCTLines] signed mantissa codes at line positions (0 where bitAlloc == 0)  codec.py:276-277 */
 } PacTrace;
 
 /* ------------------------------------------------------------------ context */
@@ -103,6 +104,7 @@ int pac_set_stream(PacCtx *ctx, void *stream);
 #define PAC_K_INDEX    3   /* decoder: chunk chain walk */
 #define PAC_K_UNPACK   4   /* decoder: bit unpack + Huffman decode + dequantise */
 #define PAC_K_SYNTH    5   /* decoder: M/S recombine + IMDCT + window + overlap-add + PCM */
+#define PAC_K_MDCT     6   /* window + MDCT + overall scale by itself (pac_mdct_batch; the MDCT-only instantiation of the analysis kernel) */
 #define PAC_NKINDS     8
 int pac_timing_enable(PacCtx *ctx, int on);                       /* also resets the accumulators */
 int pac_timing_get(PacCtx *ctx, double *ms /*[PAC_NKINDS]*/, int64_t *count /*[PAC_NKINDS]*/);
@@ -140,6 +142,17 @@ int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int
  * of pac_encode_batch decoded in place on the device (pacBeg[s] = s*cap, pacLen[s] = outBytes[s]). */
 int pac_decode_batch_strided(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg, const int64_t *pacLen, int S, int16_t *pcm,
                              int64_t strideSamples, int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate);
+/* The window + MDCT stage of pac_encode_batch by itself, over the same (stream, block) tiling: PCMFile.ReadDataBlock's
+ * int16 -> fraction (pcmfile.py:91-98), SineWindow (window.py:27-39), MDCT (mdct.py:49-71), overall scale (codec.py:237-246).
+ * pcm / strideSamples / nSamples as pac_encode_batch.  lines (host, may be NULL): [S][B][2][nMDCTLines] the scaled L/R lines
+ * (2^overallScale * MDCT), oscale (host, may be NULL): [S][B][2], B = max pac_num_blocks; with both NULL the results stay in the
+ * library's tile workspace (stage timing).  deviceMs (may be NULL): CUDA-event time of the kernel launches only. */
+int pac_mdct_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S, double *lines,
+                   int32_t *oscale, double *deviceMs);
+/* The whole analysis stage of pac_encode_batch (window + MDCT + M/S decision + stereo SMR: the k_analysis kernel) over the same
+ * tiling, by itself -- not overlapped with the scan/pack kernels as inside pac_encode_batch -- results left in the tile
+ * workspace.  For stage timing: SMR stage = this - pac_mdct_batch.  deviceMs: CUDA-event time of the kernel launches. */
+int pac_analysis_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S, double *deviceMs);
 /* upper bound of samples/channel a .pac image of nbytes can decode to */
 int64_t pac_decode_bound(PacCtx *ctx, int64_t nbytes);
 

@@ -44,7 +44,7 @@ class PacTrace(C.Structure):
     _fields_ = [("lrms", C.POINTER(C.c_int32)), ("oscale", C.POINTER(C.c_int32)), ("smr", C.POINTER(C.c_double)),
                 ("lines", C.POINTER(C.c_double)), ("ba", C.POINTER(C.c_int32)), ("sf", C.POINTER(C.c_int32)),
                 ("tableID", C.POINTER(C.c_int32)), ("nbytes", C.POINTER(C.c_int32)),
-                ("extraBits", C.POINTER(C.c_int64)), ("bitDeposit", C.POINTER(C.c_int64))]
+                ("extraBits", C.POINTER(C.c_int64)), ("bitDeposit", C.POINTER(C.c_int64)), ("mant", C.POINTER(C.c_int32))]
 
 
 class PacStreamState(C.Structure):
@@ -83,6 +83,8 @@ def lib():
     L.pac_decode_bound.argtypes = [vp, C.c_int64]
     L.pac_decode_bound.restype = C.c_int64
     L.pac_encode_batch.argtypes = [vp, vp, C.c_int64, i64p, C.c_int, vp, C.c_int64, i64p, i64p, C.POINTER(PacTrace)]
+    L.pac_mdct_batch.argtypes = [vp, vp, C.c_int64, i64p, C.c_int, dp, i32p, dp]
+    L.pac_analysis_batch.argtypes = [vp, vp, C.c_int64, i64p, C.c_int, dp]
     L.pac_decode_batch.argtypes = [vp, vp, i64p, C.c_int, vp, C.c_int64, i64p, i64p, i32p]
     L.pac_decode_batch_strided.argtypes = [vp, vp, i64p, i64p, C.c_int, vp, C.c_int64, i64p, i64p, i32p]
     L.pac_encode_blocks.argtypes = [vp, dp, C.c_int, C.POINTER(PacStreamState), i32p, i32p, i32p, i32p, i32p, i32p, u8p, C.c_int64, i32p]
@@ -125,8 +127,15 @@ class _Unpickler(pickle.Unpickler):
         if (module, name) == ("collections", "deque"):
             import collections
             return collections.deque
+        # protocol-0 pickles of new-style classes (what the trainer shim writes back under Python 3, Huffman.py:195-211) are rebuilt
+        # through copy_reg._reconstructor(cls, object, None); cls itself still has to pass the whitelist above
+        if (module, name) in (("copy_reg", "_reconstructor"), ("copyreg", "_reconstructor")):
+            import copyreg
+            return copyreg._reconstructor
+        if (module, name) in (("__builtin__", "object"), ("builtins", "object")):
+            return object
         raise pickle.UnpicklingError("refusing to unpickle %s.%s: the codec's table fixtures only hold Huffman.HuffmanTable, "
-                                     "Huffman.Histogram and collections.deque" % (module, name))
+                                     "Huffman.Histogram, Huffman.HuffmanNode and collections.deque" % (module, name))
 
 
 def safe_load(handle, classes=None):
@@ -234,7 +243,7 @@ class Engine(object):
     def launches(self):
         return int(lib().pac_launch_count(self.ctx))
 
-    KINDS = ("analysis", "scan", "pack", "index", "unpack", "synth")
+    KINDS = ("analysis", "scan", "pack", "index", "unpack", "synth", "mdct")
 
     def set_stream(self, cuda_stream_handle):
         """use the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream).  Handle 0 is CUDA's legacy default
@@ -282,11 +291,12 @@ class Engine(object):
                   "smr": np.zeros((S, B, 2, NB)), "lines": np.zeros((S, B, 2, M)),
                   "ba": np.zeros((S, B, 2, NB), np.int32), "sf": np.zeros((S, B, 2, NB), np.int32),
                   "tableID": np.zeros((S, B, 2), np.int32), "nbytes": np.zeros((S, B, 2), np.int32),
-                  "extraBits": np.zeros((S, B), np.int64), "bitDeposit": np.zeros((S, B), np.int64)}
+                  "extraBits": np.zeros((S, B), np.int64), "bitDeposit": np.zeros((S, B), np.int64),
+                  "mant": np.zeros((S, B, 2, M), np.int32)}
             trs = PacTrace(_p(tr["lrms"], C.c_int32), _p(tr["oscale"], C.c_int32), _p(tr["smr"], C.c_double),
                            _p(tr["lines"], C.c_double), _p(tr["ba"], C.c_int32), _p(tr["sf"], C.c_int32),
                            _p(tr["tableID"], C.c_int32), _p(tr["nbytes"], C.c_int32), _p(tr["extraBits"], C.c_int64),
-                           _p(tr["bitDeposit"], C.c_int64))
+                           _p(tr["bitDeposit"], C.c_int64), _p(tr["mant"], C.c_int32))
         if isinstance(pcm, np.ndarray):
             pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         rc = lib().pac_encode_batch(self.ctx, _vp(pcm), stride, _p(nSamples, C.c_int64), S, _vp(out), int(cap),
@@ -297,6 +307,33 @@ class Engine(object):
             res = [out[s, :outBytes[s]].tobytes() for s in range(S)]
             return (res, tr) if trace else res
         return (out, outBytes, tr) if trace else (out, outBytes)
+
+    def mdct_batch(self, pcm, nSamples=None, want=True):
+        """The window + MDCT stage of encode_batch by itself (pac_mdct_batch): int16 [S][n][2] -> (lines [S][B][2][M] scaled L/R
+        lines, oscale [S][B][2], device ms of the kernel launches); want=False keeps the results on the device (stage timing)."""
+        S, stride = int(pcm.shape[0]), int(pcm.shape[1])
+        if nSamples is None:
+            nSamples = np.full(S, stride, dtype=np.int64)
+        nSamples = np.ascontiguousarray(nSamples, dtype=np.int64)
+        B = max(self.num_blocks(int(n)) for n in nSamples)
+        lines = np.zeros((S, B, 2, self.M)) if want else None
+        osc = np.zeros((S, B, 2), np.int32) if want else None
+        ms = C.c_double(0.0)
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        self._ck(lib().pac_mdct_batch(self.ctx, _vp(pcm), stride, _p(nSamples, C.c_int64), S,
+                                      _p(lines, C.c_double) if want else None, _p(osc, C.c_int32) if want else None, C.byref(ms)))
+        return lines, osc, float(ms.value)
+
+    def analysis_batch_ms(self, pcm, nSamples=None):
+        """device ms of the whole analysis kernel run by itself over the batch (pac_analysis_batch; stage timing)"""
+        S, stride = int(pcm.shape[0]), int(pcm.shape[1])
+        if nSamples is None:
+            nSamples = np.full(S, stride, dtype=np.int64)
+        nSamples = np.ascontiguousarray(nSamples, dtype=np.int64)
+        ms = C.c_double(0.0)
+        self._ck(lib().pac_analysis_batch(self.ctx, _vp(pcm), stride, _p(nSamples, C.c_int64), S, C.byref(ms)))
+        return float(ms.value)
 
     def decode_bound(self, nbytes):
         return int(lib().pac_decode_bound(self.ctx, int(nbytes)))

@@ -421,7 +421,10 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
     return make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
-template <typename T, int LOGM>
+// MDCT_ONLY = true is the stage instantiation behind pac_mdct_batch: sections A + C (PCM -> fractions, SineWindow, MDCT,
+// overall scale), writing the scaled L/R lines and the overall scales, nothing else -- the window+MDCT stage of the encoder
+// measured by itself (SURVEY.md 8d asks for the MDCT and SMR roofline fractions separately).
+template <typename T, int LOGM, bool MDCT_ONLY = false>
 __global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? PAC_ANALYSIS_CTAS : 1)
 k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     using S = AnalysisSmem<T, LOGM, sizeof(T) == 4>;
@@ -592,7 +595,14 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
             }
         };
-        if constexpr (FAST) sectionC();       // fp32: MDCT first, while x is still in shared memory (the FFT batch below runs in place)
+        if constexpr (FAST || MDCT_ONLY) sectionC();   // fp32: MDCT first, while x is still in shared memory (the FFT batch below runs in place)
+        if constexpr (MDCT_ONLY) {
+            __syncthreads();
+            for (int e = tid; e < 2 * M; e += NT) a.lines[w * 2 * M + e] = sm.Lb[e / M][e % M];
+            if (tid < 2) a.oscale[w * 2 + tid] = (uint8_t)(tid ? osc1 : osc0);
+            __syncthreads();
+            continue;
+        }
         // ------------------------------------------------ B. raw FFTs -> LRMS decision (codec.py:96-102)
         // fp64: raw FFTs of L, R in W.  fp32: the raw FFTs run IN PLACE in XF and, in the same batch of four, the FFTs of the
         // sine*Hann windowed channels in W (the fp32 MDCT has already consumed x).
@@ -639,7 +649,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             }
             __syncthreads();
         }
-        if constexpr (!FAST) sectionC();
+        if constexpr (!FAST && !MDCT_ONLY) sectionC();
         if constexpr (!FAST) {
             // ------------------------------------------------ D. Hann on the sine-windowed data (psychoac.py:428) + FFT
             for (int e = tid; e < 2 * M; e += NT) {

@@ -669,6 +669,25 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     return PAC_OK;
 }
 
+// the MDCT-only stage instantiation (sections A + C): persistent grid, the part of the shared-memory struct it touches
+template <typename T, int LOGM>
+static int launch_mdct_only_t(PacCtx *ctx, AnalysisArgs<T> &a) {
+    using SM = AnalysisSmem<T, LOGM, sizeof(T) == 4>;
+    const size_t smem = offsetof(SM, fs);
+    a.poisonOn = 0; a.poison = 0; a.smemWords = 0;
+    CK(cudaFuncSetAttribute(k_analysis<T, LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSM = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM, true>, (1 << LOGM) / 4, smem));
+    if (perSM < 1) perSM = 1;
+    int64_t grid = (int64_t)ctx->numSMs * perSM;
+    if (grid > a.nwork) grid = a.nwork;
+    if (grid < 1) grid = 1;
+    { KTimer kt(ctx, PAC_K_MDCT); k_analysis<T, LOGM, true><<<(unsigned)grid, (1 << LOGM) / 4, smem, LS(ctx)>>>(a); }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
 template <typename T>
 static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
     a.bands = ctx->bands;
@@ -691,8 +710,17 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         if (rc) return rc;
         a.band_of_line = tb.band_of_line;
     }
-    // one CTA of kScanWarps warps per stream: warp 0 carries the serial state, all warps share the line phase (scan.cuh)
-    { KTimer kt(ctx, PAC_K_SCAN); k_scan<T, kScanWarps><<<a.S, kScanWarps * 32, 0, LS(ctx)>>>(a); }
+    // one CTA per stream: warp 0 carries the serial state, all warps share the line phase (scan.cuh).  Many streams: the kernel is
+    // a throughput problem and runs beside k_analysis, where a CTA's register-time is what it costs -> 2 warps; few streams (a
+    // shard of the 8-GPU run): the per-stream chain is what matters -> 8 warps.  Results do not depend on the choice.
+    int warps = a.S >= 1536 ? 2 : (a.S >= 768 ? 4 : 8);
+    if (const char *we = getenv("PAC_SCAN_WARPS")) { const int v = atoi(we); if (v == 2 || v == 4 || v == 8) warps = v; }
+    {
+        KTimer kt(ctx, PAC_K_SCAN);
+        if (warps == 2) k_scan<T, 2><<<a.S, 64, 0, LS(ctx)>>>(a);
+        else if (warps == 4) k_scan<T, 4><<<a.S, 128, 0, LS(ctx)>>>(a);
+        else k_scan<T, 8><<<a.S, 256, 0, LS(ctx)>>>(a);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -930,6 +958,11 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
             pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = d_out; pa.cap = cap; pa.perChunk = 0;
             pa.overflow = ctx->w_ovf.template as<int>() + s0; pa.o_mant = nullptr;
+            if (trace && trace->mant) {
+                CK(ctx->w_misc.ensure((size_t)nwork * 2 * M * 4));
+                CK(cudaMemsetAsync(ctx->w_misc.p, 0, (size_t)nwork * 2 * M * 4, sB));
+                pa.o_mant = ctx->w_misc.template as<int32_t>();
+            }
             pa.header = ctx->w_hdr.template as<uint8_t>() + (size_t)s0 * hdrB; pa.headerBytes = hdrB;
             rc = launch_pack<T>(ctx, pa);
             ctx->launchStream = nullptr;
@@ -942,6 +975,8 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
                 std::vector<uint8_t> hba((size_t)nwork * 2 * kMaxBands), hsf((size_t)nwork * 2 * kMaxBands), htid((size_t)nwork * 2), hosc((size_t)nwork * 2);
                 std::vector<uint32_t> hlr(nwork), hnby((size_t)nwork * 2);
                 std::vector<long long> hE(nwork), hD(nwork);
+                std::vector<int32_t> hm;
+                if (trace->mant) { hm.resize((size_t)nwork * 2 * M); CK(cudaMemcpy(hm.data(), pa.o_mant, hm.size() * 4, cudaMemcpyDeviceToHost)); }
                 if (trace->lines) { hl.resize((size_t)nwork * 2 * M); CK(cudaMemcpy(hl.data(), aa.lines, hl.size() * sizeof(T), cudaMemcpyDeviceToHost)); }
                 if (trace->smr) { hs.resize((size_t)nwork * 2 * kMaxBands); CK(cudaMemcpy(hs.data(), aa.smr, hs.size() * sizeof(T), cudaMemcpyDeviceToHost)); }
                 CK(cudaMemcpy(hba.data(), sa.ba, hba.size(), cudaMemcpyDeviceToHost));
@@ -970,6 +1005,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
                             }
                             if (trace->lines)
                                 for (int i = 0; i < M; i++) trace->lines[(gi * 2 + ch) * M + i] = (double)hl[(w * 2 + ch) * M + i];
+                            if (trace->mant) memcpy(trace->mant + (gi * 2 + ch) * M, hm.data() + (w * 2 + ch) * M, (size_t)M * 4);
                         }
                     }
                 }
@@ -1203,6 +1239,102 @@ extern "C" int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *
     std::vector<int64_t> len(S);
     for (int s = 0; s < S; s++) len[s] = pacOff[s + 1] - pacOff[s];
     return pac_decode_batch_strided(ctx, pac, pacOff, len.data(), S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+}
+
+// ------------------------------------------------------------------ window + MDCT stage by itself (whole streams)
+template <typename T>
+static int mdct_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const int64_t *nSamples, int S, double *lines, int32_t *oscale,
+                        double *deviceMs, bool full = false) {
+    const int M = ctx->M;
+    const bool pcmDev = is_device_ptr(pcm);
+    int64_t maxBlocks = 0;
+    for (int s = 0; s < S; s++) {
+        if (nSamples[s] < 0 || nSamples[s] > stride) FAIL(PAC_E_ARG, "nSamples[%d] outside [0, strideSamples]", s);
+        const int64_t nb = pac_num_blocks(ctx, nSamples[s]);
+        if (nb > maxBlocks) maxBlocks = nb;
+    }
+    const int16_t *d_pcm = pcm;
+    if (!pcmDev) {
+        CK(ctx->w_pcm.ensure((size_t)S * stride * 4 + 16));
+        CK(cudaMemcpyAsync(ctx->w_pcm.p, pcm, (size_t)S * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_pcm = ctx->w_pcm.as<int16_t>();
+    }
+    CK(ctx->w_ns.ensure((size_t)S * 8));
+    CK(cudaMemcpyAsync(ctx->w_ns.p, nSamples, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int TB = (int)(((int64_t)1 << 18) / S);                   // the encoder's tile budget: 2^18 (stream, block) items
+    if (TB < 1) TB = 1;
+    if (TB > maxBlocks) TB = (int)maxBlocks;
+    const int64_t nworkMax = (int64_t)S * TB;
+    CK(ctx->w_lines.ensure((size_t)nworkMax * 2 * M * sizeof(T)));
+    CK(ctx->w_osc.ensure((size_t)nworkMax * 2));
+    if (full) {
+        CK(ctx->w_smr.ensure((size_t)nworkMax * 2 * kMaxBands * sizeof(T)));
+        CK(ctx->w_bmax.ensure((size_t)nworkMax * 2 * kMaxBands * sizeof(T)));
+        CK(ctx->w_lrms.ensure((size_t)nworkMax * 4));
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float total = 0.f;
+    std::vector<T> hl;
+    std::vector<uint8_t> ho;
+    for (int64_t b0 = 0; b0 < maxBlocks; b0 += TB) {
+        const int nb = (int)(maxBlocks - b0 < TB ? maxBlocks - b0 : TB);
+        AnalysisArgs<T> aa{};
+        aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.as<int64_t>(); aa.blocks = nullptr;
+        aa.S = S; aa.b0 = (int)b0; aa.nb = nb; aa.nwork = (int64_t)S * nb;
+        aa.lines = ctx->w_lines.as<T>(); aa.oscale = ctx->w_osc.as<uint8_t>();
+        aa.bands = ctx->bands; aa.nScaleBits = ctx->p.nScaleBits;
+        int rc = get_tables<T>(ctx, ctx->N, &aa.tab);
+        if (rc) return rc;
+        if ((rc = get_tables<double>(ctx, ctx->N, &aa.tabd))) return rc;
+        if (full) { aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>(); aa.lrms = ctx->w_lrms.as<uint32_t>(); }
+        CK(cudaEventRecord(e0, ctx->stream));
+        if (full) rc = launch_analysis<T>(ctx, aa);           // the whole analysis kernel, by itself (persistent grid)
+        else if (ctx->LOGM == 10) rc = launch_mdct_only_t<T, 10>(ctx, aa);
+        else rc = launch_mdct_only_t<T, 9>(ctx, aa);
+        if (rc) return rc;
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+        if (lines || oscale) {
+            hl.resize((size_t)aa.nwork * 2 * M); ho.resize((size_t)aa.nwork * 2);
+            CK(cudaMemcpy(hl.data(), aa.lines, hl.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ho.data(), aa.oscale, ho.size(), cudaMemcpyDeviceToHost));
+            for (int s = 0; s < S; s++) {
+                const int64_t nbs = pac_num_blocks(ctx, nSamples[s]);
+                for (int64_t b = b0; b < b0 + nb && b < nbs; b++) {
+                    const int64_t w = (int64_t)s * nb + (b - b0), gi = (int64_t)s * maxBlocks + b;
+                    for (int ch = 0; ch < 2; ch++) {
+                        if (oscale) oscale[gi * 2 + ch] = ho[w * 2 + ch];
+                        if (lines) for (int i = 0; i < M; i++) lines[(gi * 2 + ch) * M + i] = (double)hl[(w * 2 + ch) * M + i];
+                    }
+                }
+            }
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (deviceMs) *deviceMs = (double)total;
+    return PAC_OK;
+}
+
+extern "C" int pac_mdct_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S, double *lines,
+                              int32_t *oscale, double *deviceMs) {
+    if (!ctx) return PAC_E_ARG;
+    if (!pcm || !nSamples || S <= 0 || strideSamples < 0) FAIL(PAC_E_ARG, "bad arguments to pac_mdct_batch");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return mdct_batch_t<double>(ctx, pcm, strideSamples, nSamples, S, lines, oscale, deviceMs);
+    return mdct_batch_t<float>(ctx, pcm, strideSamples, nSamples, S, lines, oscale, deviceMs);
+}
+
+extern "C" int pac_analysis_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S, double *deviceMs) {
+    if (!ctx) return PAC_E_ARG;
+    if (!pcm || !nSamples || S <= 0 || strideSamples < 0) FAIL(PAC_E_ARG, "bad arguments to pac_analysis_batch");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->precision == PAC_PRECISION_FP64) return mdct_batch_t<double>(ctx, pcm, strideSamples, nSamples, S, nullptr, nullptr, deviceMs, true);
+    return mdct_batch_t<float>(ctx, pcm, strideSamples, nSamples, S, nullptr, nullptr, deviceMs, true);
 }
 
 // ------------------------------------------------------------------ per-block API

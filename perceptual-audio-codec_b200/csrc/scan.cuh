@@ -10,8 +10,6 @@
 
 namespace pac {
 
-constexpr int kScanWarps = 8;     // warps per stream CTA of k_scan (half of them per channel in the line phase)
-
 struct StreamState {
     long long extraBits;     // cp.extraBits
     long long bitDeposit;    // huffman.bitDeposit
@@ -214,23 +212,33 @@ k_scan(const ScanArgs<T> a) {
         bandsPacked[q] = v;
     }
 
+    // warp 0: band inputs of a block are fetched one block ahead (their latency would otherwise sit on the serial chain)
+    uint32_t lrmsN = 0;
+    T smrN[2] = {0, 0}, bmaxN[2] = {0, 0};
+    auto fetchBands = [&](int b) {
+        const int64_t w = (int64_t)s * a.nb + (b - a.b0);
+        lrmsN = a.lrms[w];
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            smrN[ch] = lane < NB ? a.smr[(w * 2 + ch) * kMaxBands + lane] : (T)0;
+            bmaxN[ch] = lane < NB ? a.bmax[(w * 2 + ch) * kMaxBands + lane] : (T)0;
+        }
+    };
+    if (warp == 0 && a.b0 < bEnd) fetchBands(a.b0);
+
     for (int b = a.b0; b < bEnd; b++) {
         const int64_t w = (int64_t)s * a.nb + (b - a.b0);
-        // every warp: its lines of this block (they do not depend on the allocation)
-        T xv[LPLMAX];
-        {
-            const T *x = a.lines + (w * 2 + myCh) * M + l0 + lane;
+        // every warp: the first chunk of its lines of this block (they do not depend on the allocation), so that their
+        // latency hides behind the BitAllocs; further chunks (fewer warps per stream) are fetched one chunk ahead below
+        constexpr int CH = WARPS >= 8 ? (LPLMAX < 8 ? LPLMAX : 8) : 4;   // lines per lane per chunk (fewer in flight where registers count)
+        const T *xrow = a.lines + (w * 2 + myCh) * M + l0 + lane;
+        T xv[CH];
 #pragma unroll
-            for (int j = 0; j < LPLMAX; j++) xv[j] = j < lpl ? x[j * 32] : (T)0;
-        }
+        for (int j = 0; j < CH; j++) xv[j] = j < lpl ? xrow[j * 32] : (T)0;
         if (warp == 0) {
-            const uint32_t lrms = a.lrms[w];
-            T smrL[2], bmaxL[2];
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                smrL[ch] = lane < NB ? a.smr[(w * 2 + ch) * kMaxBands + lane] : (T)0;
-                bmaxL[ch] = lane < NB ? a.bmax[(w * 2 + ch) * kMaxBands + lane] : (T)0;
-            }
+            const uint32_t lrms = lrmsN;
+            const T smrL[2] = {smrN[0], smrN[1]}, bmaxL[2] = {bmaxN[0], bmaxN[1]};
+            if (b + 1 < bEnd) fetchBands(b + 1);
             // withdrawBits, Huffman.py:363-371 (floor division of a positive int)
             {
                 long long extra = 0;
@@ -258,18 +266,32 @@ k_scan(const ScanArgs<T> a) {
         {
             unsigned long long acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int j = 0; j < LPLMAX; j++) {
-                if (j < lpl) {
-                    const int bd = (bandsPacked[j >> 2] >> (8 * (j & 3))) & 0xff;
-                    const unsigned bs = sBitsSf[myCh][bd];
-                    const int bab = (int)(bs & 0xffu), sfb = (int)(bs >> 8);
-                    if (bab > 0) {
-                        unsigned mag = mant_mag(fabs((double)xv[j]), sfb, largestScale, bab);
-                        const ulonglong2 *ep = reinterpret_cast<const ulonglong2 *>(a.lenLut4 + (mag < (unsigned)kLenLutSize ? mag : (unsigned)kLenLutSize));
-                        const ulonglong2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
-                        acc0 += e0.x + e1.x * (unsigned long long)bab;
-                        acc1 += e0.y + e1.y * (unsigned long long)bab;
+            for (int c0 = 0; c0 < LPLMAX; c0 += CH) {
+                if (c0 >= lpl) break;
+                T xn[CH];
+                if (c0 + CH < LPLMAX) {
+#pragma unroll
+                    for (int j = 0; j < CH; j++) xn[j] = c0 + CH + j < lpl ? xrow[(c0 + CH + j) * 32] : (T)0;
+                }
+#pragma unroll
+                for (int jj = 0; jj < CH; jj++) {
+                    const int j = c0 + jj;
+                    if (j < lpl) {
+                        const int bd = (bandsPacked[j >> 2] >> (8 * (j & 3))) & 0xff;
+                        const unsigned bs = sBitsSf[myCh][bd];
+                        const int bab = (int)(bs & 0xffu), sfb = (int)(bs >> 8);
+                        if (bab > 0) {
+                            unsigned mag = mant_mag(fabs((double)xv[jj]), sfb, largestScale, bab);
+                            const ulonglong2 *ep = reinterpret_cast<const ulonglong2 *>(a.lenLut4 + (mag < (unsigned)kLenLutSize ? mag : (unsigned)kLenLutSize));
+                            const ulonglong2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+                            acc0 += e0.x + e1.x * (unsigned long long)bab;
+                            acc1 += e0.y + e1.y * (unsigned long long)bab;
+                        }
                     }
+                }
+                if (c0 + CH < LPLMAX) {
+#pragma unroll
+                    for (int j = 0; j < CH; j++) xv[j] = xn[j];
                 }
             }
 #pragma unroll
