@@ -50,21 +50,18 @@ struct DevTables {
 };
 
 // Static geometry + scan weights of the fp32 fast threshold evaluation (analysis.cuh: masked_curve_fast; numpy model
-// in tests/model_analysis.py: Geometry / weighted_suffix_scan / curve_v2).  NT = M/4 "virtual threads" own 4
-// consecutive lines each; chunk = 128 lines = one warp.
+// in tests/model_analysis.py: Geometry / weighted_suffix_scan / curve_v3).  The fixed-slope skirts are scans over the BINS
+// (Bark positions zp_k of the masker frequencies k * (fs // N)): NT = M/4 threads own 4 consecutive bins each, a warp 128.
 struct FastTables {
-    const short *eL, *eU;        // [M] per bin: last line of its lower skirt (-1: none) / first line of its upper skirt (M: none)
-    const float *xL, *xU;        // [M] per bin: dn * (Bark gap from the skirt origin to that entry line)  (exponent, <= 0)
-    const short *lineTab;        // [6][M] per line: kLa,nL (bins entering the down-scan here), kUa,nU (up-scan), pa,pb (plateau bins)
-    const short *kcountU;        // [M+1] kcountU[i] = number of bins with eU <= i-1 ... see host builder (prefix over lines)
-    const float4 *binTab;        // [M] per bin: (xL, xU, zpeak_hi, zpeak_lo)
-    const uint4 *binEU;          // [NT] per thread, per bin: (uint16)eL | eU << 16
+    const uint2 *binEU;          // [NT] per thread: first line of the upper skirt (M: none) of its four bins, 16 bits each
+    const float2 *binZ;          // [M] per bin: Bark position of the masker frequency as hi + lo floats
+    const float4 *lineRec;       // [M] per line: (pa | pb << 16 as bits, fL, fU, threshold in quiet) -- plateau bins [pa, pb);
+                                 //     lower skirts = SD[min(pb, M-1)] * fL, quiet upper skirts = SA[max(pa-1, 0)] * fU
     const float2 *lineZ;         // [M] per line: Bark position as hi + lo floats
-    const uint4 *lineGather;     // [NT] per scan thread, per line: kLa | nL << 10 | kUa << 12 | nU << 22
-    const uint4 *linePlat;       // [NT] per scan thread, per line: pa | pb << 16 (plateau bin window)
+    const short *kcountU;        // [M+1] kcountU[i] = number of bins whose upper skirt starts at or before line i
     const float *sD;             // [13][NT] descending scan weights: wl[3], ww[5], wc, wf[4]
     const float *sA;             // [10][NT] ascending scan weights: ww[5], wc, wf[4]
-    float omD[16], omA[16];      // per-chunk carry weights
+    float omD[16], omA[16];      // per-warp carry weights
 };
 
 // Encoder scalars derived from PacParams

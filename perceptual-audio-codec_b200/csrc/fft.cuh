@@ -76,14 +76,113 @@ __device__ __forceinline__ void fft_dif(typename Vec2<T>::type *buf, int nbatch,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Register-blocked 1024-point FFT (fp32 batch of the analysis kernel): radix 16 x 16 x 4, in place, decimation in
+// frequency.  A thread holds 16 points in registers and does a whole 16-point DFT (two levels of radix-4 butterflies with the
+// W16 twiddles as constants) between one shared-memory read and one write: three passes through shared memory and three
+// barriers instead of the five of the radix-4 version, and the index/twiddle-address arithmetic is paid per 16 points
+// instead of per 4 (ncu, round 1: the FFT butterflies + complex helpers were 17.7 % of the analysis kernel's instructions).
+//   pass 1: elements j + 64 r            (j < 64)            twiddle W_1024^(j p)
+//   pass 2: elements 64 g + j + 4 r      (g < 16, j < 4)     twiddle W_64^(j p)
+//   pass 3: radix 4 on 4 consecutive elements, no twiddle
+// Frequency k = p1 + 16 p2 + 256 p3 ends at position 64 p1 + 4 p2 + p3 (fft_pos1024 below).  With the padded layout
+// (one spare element per 16) every pass is conflict-free for 64-bit accesses.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fft_pos1024(int k) { return ((k & 15) << 6) | (((k >> 4) & 15) << 2) | (k >> 8); }
+
+// frequency k of the fp32 batch FFTs (1024-point: register-blocked order; otherwise the radix-4 order)
+template <int LOGN, bool R16>
+__device__ __forceinline__ int fft_pos_sel(int k) {
+    if constexpr (R16 && LOGN == 10) return fft_pos1024(k);
+    else return fft_pos<LOGN>(k);
+}
+
+__device__ __forceinline__ void radix4_f(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    const float2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), d = csub(a1, a3);
+    const float2 b3 = make_float2(d.y, -d.x);                  // -i (a1 - a3)
+    a0 = cadd(b0, b2); a2 = csub(b0, b2); a1 = cadd(b1, b3); a3 = csub(b1, b3);
+}
+
+// in-register 16-point DFT: y[d + 4c] (natural order) from x[a + 4b]
+__device__ __forceinline__ void dft16_f(float2 (&x)[16]) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+#pragma unroll
+    for (int a = 0; a < 4; a++) radix4_f(x[a], x[a + 4], x[a + 8], x[a + 12]);     // t[a][d] sits in x[a + 4 d]
+    // twiddles W16^(a d), a, d = 1..3
+    x[1 + 4] = cmul(x[1 + 4], make_float2(C1, -S1));           // a=1,d=1: W^1
+    x[1 + 8] = cmul(x[1 + 8], make_float2(H, -H));             // a=1,d=2: W^2
+    x[1 + 12] = cmul(x[1 + 12], make_float2(S1, -C1));         // a=1,d=3: W^3
+    x[2 + 4] = cmul(x[2 + 4], make_float2(H, -H));             // a=2,d=1: W^2
+    x[2 + 8] = make_float2(x[2 + 8].y, -x[2 + 8].x);           // a=2,d=2: W^4 = -i
+    x[2 + 12] = cmul(x[2 + 12], make_float2(-H, -H));          // a=2,d=3: W^6
+    x[3 + 4] = cmul(x[3 + 4], make_float2(S1, -C1));           // a=3,d=1: W^3
+    x[3 + 8] = cmul(x[3 + 8], make_float2(-H, -H));            // a=3,d=2: W^6
+    x[3 + 12] = cmul(x[3 + 12], make_float2(-C1, S1));         // a=3,d=3: W^9
+#pragma unroll
+    for (int d = 0; d < 4; d++) radix4_f(x[4 * d], x[4 * d + 1], x[4 * d + 2], x[4 * d + 3]);   // -> y[d + 4c] in x[4 d + c]
+}
+
+// buf: nbatch transforms of 1024 points (padded layout when PAD), transform b at buf + b*bstride.  tw[m] = exp(-2 pi i m / 1024).
+template <int NTHREADS, bool PAD>
+__device__ __forceinline__ void fft1024_r16(float2 *buf, int nbatch, int bstride, const float2 *__restrict__ tw) {
+    const int tid = threadIdx.x;
+    // ---- pass 1
+    for (int w = tid; w < nbatch * 64; w += NTHREADS) {
+        const int bt = w >> 6, j = w & 63;
+        float2 *p = buf + bt * bstride;
+        float2 x[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) x[r] = p[fft_pad<PAD>(j + 64 * r)];
+        dft16_f(x);
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int pp = d + 4 * c;                       // output index of x[4 d + c]
+                float2 y = x[4 * d + c];
+                if (pp) y = cmul(y, tw[j * pp]);
+                p[fft_pad<PAD>(j + 64 * pp)] = y;
+            }
+    }
+    __syncthreads();
+    // ---- pass 2
+    for (int w = tid; w < nbatch * 64; w += NTHREADS) {
+        const int bt = w >> 6, g = (w >> 2) & 15, j = w & 3;
+        float2 *p = buf + bt * bstride;
+        float2 x[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) x[r] = p[fft_pad<PAD>(64 * g + j + 4 * r)];
+        dft16_f(x);
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int pp = d + 4 * c;
+                float2 y = x[4 * d + c];
+                if (pp) y = cmul(y, tw[16 * j * pp]);
+                p[fft_pad<PAD>(64 * g + j + 4 * pp)] = y;
+            }
+    }
+    __syncthreads();
+    // ---- pass 3: radix 4 on consecutive elements
+    for (int w = tid; w < nbatch * 256; w += NTHREADS) {
+        const int bt = w >> 8, g = w & 255;
+        float2 *p = buf + bt * bstride + fft_pad<PAD>(4 * g);  // 4 g .. 4 g + 3 never straddle a pad (16 | 4 g + 4 only at the end)
+        float2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+        radix4_f(a0, a1, a2, a3);
+        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+    }
+    __syncthreads();
+}
+
 // X[k] (0 <= k <= M) of a real sequence whose packed (even + i*odd) M-point FFT sits in Z (digit-reversed).
-template <typename T, int LOGM, bool PAD = false>
+template <typename T, int LOGM, bool PAD = false, bool R16 = false>
 __device__ __forceinline__ typename Vec2<T>::type rfft_split(const typename Vec2<T>::type *Z, int k,
                                                              const typename Vec2<T>::type *__restrict__ tw_split) {
     using T2 = typename Vec2<T>::type;
     constexpr int Mm = (1 << LOGM) - 1;
-    T2 zk = Z[fft_pad<PAD>(fft_pos<LOGM>(k & Mm))];
-    T2 zm = cconj(Z[fft_pad<PAD>(fft_pos<LOGM>(((1 << LOGM) - k) & Mm))]);
+    T2 zk = Z[fft_pad<PAD>(fft_pos_sel<LOGM, R16>(k & Mm))];
+    T2 zm = cconj(Z[fft_pad<PAD>(fft_pos_sel<LOGM, R16>(((1 << LOGM) - k) & Mm))]);
     T2 e = cadd(zk, zm), d = csub(zk, zm);
     e.x *= (T)0.5; e.y *= (T)0.5;
     T2 o = mk2<T>(d.y * (T)0.5, -d.x * (T)0.5);      // (zk - conj(zm)) / (2i)

@@ -289,8 +289,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         zp[i] = h_bark((double)i * (double)(fs / N));
     }
     const double dn = -27.0 * (log2(10.0) / 10.0);
-    std::vector<short> eL(M), eU(M), lineTab(6 * M), kcountU(M + 1);
-    std::vector<float> xL(M), xU(M);
+    std::vector<int> eL(M), eU(M);
     for (int k = 0; k < M; k++) {
         int el = -1, eu = M;
         for (int i = 0; i < M; i++) {
@@ -298,50 +297,43 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
             if (dz < -0.5) el = i;                         // |dz| > .5 exactly as psychoac.py:116
             if (dz > 0.5 && eu == M) eu = i;
         }
-        eL[k] = (short)el; eU[k] = (short)eu;
-        xL[k] = el >= 0 ? (float)(dn * (zp[k] - 0.5 - zl[el])) : 0.f;
-        xU[k] = eu < M ? (float)(dn * (zl[eu] - zp[k] - 0.5)) : 0.f;
+        eL[k] = el; eU[k] = eu;
     }
     for (int k = 1; k < M; k++)
-        if (eL[k] < eL[k - 1] || eU[k] < eU[k - 1]) FAIL(PAC_E_ARG, "Bark tables are not monotone");
+        if (eL[k] < eL[k - 1] || eU[k] < eU[k - 1] || zp[k] < zp[k - 1]) FAIL(PAC_E_ARG, "Bark tables are not monotone");
+    if (M > 32767) FAIL(PAC_E_ARG, "fast tables pack indices in 16 bits");
+    // per line: plateau window [pa, pb) = bins with eL[k] < i < eU[k]; bins below pa reach the line with their upper skirt, bins
+    // from pb on with their lower skirt.  Static factors from the scan entry to the line (exponents <= 0).
+    std::vector<float> lineRec(4 * (size_t)M), lineZ(2 * (size_t)M), binZ(2 * (size_t)M);
+    std::vector<short> kcountU(M + 1);
     for (int i = 0; i < M; i++) {
-        int kLa = 0, kLb = 0, kUa = 0, kUb = 0, pa = 0, pb = 0, cu = 0;
+        int pa = 0, pb = 0;
         for (int k = 0; k < M; k++) {
-            if (eL[k] < i) kLa = k + 1;
-            if (eL[k] <= i) kLb = k + 1;
-            if (eU[k] < i) kUa = k + 1;
-            if (eU[k] <= i) { kUb = k + 1; cu = k + 1; }
-            if (eU[k] <= i) pa = k + 1;                    // plateau of line i: eL[k] < i < eU[k]
+            if (eU[k] <= i) pa = k + 1;
             if (eL[k] < i) pb = k + 1;
         }
-        if (kLb - kLa > 3 || kUb - kUa > 3) FAIL(PAC_E_ARG, "more than 3 bins enter a scan at one line");
-        lineTab[0 * M + i] = (short)kLa; lineTab[1 * M + i] = (short)(kLb - kLa);
-        lineTab[2 * M + i] = (short)kUa; lineTab[3 * M + i] = (short)(kUb - kUa);
-        lineTab[4 * M + i] = (short)pa;  lineTab[5 * M + i] = (short)pb;
-        kcountU[i] = (short)cu;
+        const uint32_t pk = (uint32_t)pa | ((uint32_t)pb << 16);
+        float fL = 0.f, fU = 0.f;
+        if (pb < M) { const double e = dn * (zp[pb] - 0.5 - zl[i]); if (e > 1e-9) FAIL(PAC_E_ARG, "lower-skirt factor > 1"); fL = (float)exp2(e); }
+        if (pa > 0) { const double e = dn * (zl[i] - zp[pa - 1] - 0.5); if (e > 1e-9) FAIL(PAC_E_ARG, "upper-skirt factor > 1"); fU = (float)exp2(e); }
+        memcpy(&lineRec[4 * (size_t)i], &pk, 4);
+        lineRec[4 * (size_t)i + 1] = fL; lineRec[4 * (size_t)i + 2] = fU;
+        lineRec[4 * (size_t)i + 3] = (float)pow(10.0, (h_thresh(fs / 2.0 / M * (i + 0.5)) - 96) / 10);      // psychoac.py:437
+        kcountU[i] = (short)pa;                            // bins with eU <= i
+        const float lh = (float)zl[i];
+        lineZ[2 * (size_t)i] = lh; lineZ[2 * (size_t)i + 1] = (float)(zl[i] - (double)lh);
+        const float zh = (float)zp[i];
+        binZ[2 * (size_t)i] = zh; binZ[2 * (size_t)i + 1] = (float)(zp[i] - (double)zh);
     }
     kcountU[M] = (short)M;
-    std::vector<unsigned> lineGather(M), linePlat(M);
-    for (int i = 0; i < M; i++) {
-        lineGather[i] = (unsigned)lineTab[0 * M + i] | ((unsigned)lineTab[1 * M + i] << 10) | ((unsigned)lineTab[2 * M + i] << 12) |
-                        ((unsigned)lineTab[3 * M + i] << 22);
-        linePlat[i] = (unsigned)lineTab[4 * M + i] | ((unsigned)lineTab[5 * M + i] << 16);
-    }
-    if (M > 1024) FAIL(PAC_E_ARG, "fast tables pack bin indices in 10 bits");
-    std::vector<unsigned> binEU(M);
-    for (int k = 0; k < M; k++) binEU[k] = ((unsigned)(unsigned short)eL[k]) | ((unsigned)(unsigned short)eU[k] << 16);
-    std::vector<float> binTab(4 * M), lineZ(2 * M);
-    for (int k = 0; k < M; k++) {
-        float zh = (float)zp[k];
-        binTab[4 * k + 0] = xL[k]; binTab[4 * k + 1] = xU[k]; binTab[4 * k + 2] = zh; binTab[4 * k + 3] = (float)(zp[k] - (double)zh);
-        float lh = (float)zl[k];
-        lineZ[2 * k] = lh; lineZ[2 * k + 1] = (float)(zl[k] - (double)lh);
-    }
+    std::vector<unsigned short> binEU(M);
+    for (int k = 0; k < M; k++) binEU[k] = (unsigned short)eU[k];
+    // scan weights between bins
     auto om = [&](int i, int j) -> float {
         if (i < 0 || j < 0 || i >= M || j >= M) return 0.f;
-        return (float)exp2(dn * fabs(zl[j] - zl[i]));
+        return (float)exp2(dn * fabs(zp[j] - zp[i]));
     };
-    std::vector<float> sD(13 * NT), sA(10 * NT);
+    std::vector<float> sD(13 * (size_t)NT), sA(10 * (size_t)NT);
     for (int vt = 0; vt < NT; vt++) {
         const int lane = vt & 31, chunk = vt >> 5, b = 4 * vt;
         for (int q = 0; q < 3; q++) sD[q * NT + vt] = om(b + q, b + q + 1);
@@ -357,27 +349,20 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
         fsd.dev.omD[c] = (c + 1 < NW) ? om(128 * c, 128 * (c + 1)) : 0.f;
         fsd.dev.omA[c] = (c >= 1 && c < NW) ? om(128 * c - 1, 128 * c + 127) : 0.f;
     }
-    size_t bytes = (size_t)M * 2 * 2 + (size_t)M * 4 * 2 + (size_t)6 * M * 2 + (size_t)(M + 1) * 2 + 64 + (sD.size() + sA.size()) * 4 + 64 +
-                   binTab.size() * 4 + lineZ.size() * 4 + (lineGather.size() + linePlat.size() + binEU.size()) * 4 + 256;
-    std::vector<unsigned char> host(bytes + 256, 0);
+    size_t bytes = lineRec.size() * 4 + lineZ.size() * 4 + binZ.size() * 4 + (size_t)(M + 1) * 2 + (size_t)M * 2 + (sD.size() + sA.size()) * 4 + 512;
+    std::vector<unsigned char> host(bytes, 0);
     size_t o = 0;
     auto put = [&](const void *src, size_t n) { o = (o + 15) & ~(size_t)15; memcpy(host.data() + o, src, n); size_t r = o; o += n; return r; };
-    size_t o_eL = put(eL.data(), M * 2), o_eU = put(eU.data(), M * 2), o_xL = put(xL.data(), M * 4), o_xU = put(xU.data(), M * 4);
-    size_t o_lt = put(lineTab.data(), 6 * M * 2), o_kc = put(kcountU.data(), (M + 1) * 2);
+    size_t o_lr = put(lineRec.data(), lineRec.size() * 4), o_lz = put(lineZ.data(), lineZ.size() * 4), o_bz = put(binZ.data(), binZ.size() * 4);
+    size_t o_kc = put(kcountU.data(), (size_t)(M + 1) * 2), o_be = put(binEU.data(), (size_t)M * 2);
     size_t o_sD = put(sD.data(), sD.size() * 4), o_sA = put(sA.data(), sA.size() * 4);
-    size_t o_bt = put(binTab.data(), binTab.size() * 4), o_lz = put(lineZ.data(), lineZ.size() * 4);
-    size_t o_lg = put(lineGather.data(), lineGather.size() * 4), o_lp = put(linePlat.data(), linePlat.size() * 4);
-    size_t o_be = put(binEU.data(), binEU.size() * 4);
     CK(cudaMalloc(&fsd.mem, o + 16));
     CK(cudaMemcpy(fsd.mem, host.data(), o, cudaMemcpyHostToDevice));
     unsigned char *d = reinterpret_cast<unsigned char *>(fsd.mem);
-    fsd.dev.eL = reinterpret_cast<const short *>(d + o_eL); fsd.dev.eU = reinterpret_cast<const short *>(d + o_eU);
-    fsd.dev.xL = reinterpret_cast<const float *>(d + o_xL); fsd.dev.xU = reinterpret_cast<const float *>(d + o_xU);
-    fsd.dev.lineTab = reinterpret_cast<const short *>(d + o_lt); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
+    fsd.dev.lineRec = reinterpret_cast<const float4 *>(d + o_lr); fsd.dev.lineZ = reinterpret_cast<const float2 *>(d + o_lz);
+    fsd.dev.binZ = reinterpret_cast<const float2 *>(d + o_bz); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
+    fsd.dev.binEU = reinterpret_cast<const uint2 *>(d + o_be);
     fsd.dev.sD = reinterpret_cast<const float *>(d + o_sD); fsd.dev.sA = reinterpret_cast<const float *>(d + o_sA);
-    fsd.dev.binTab = reinterpret_cast<const float4 *>(d + o_bt); fsd.dev.lineZ = reinterpret_cast<const float2 *>(d + o_lz);
-    fsd.dev.binEU = reinterpret_cast<const uint4 *>(d + o_be);
-    fsd.dev.lineGather = reinterpret_cast<const uint4 *>(d + o_lg); fsd.dev.linePlat = reinterpret_cast<const uint4 *>(d + o_lp);
     return PAC_OK;
 }
 
@@ -629,6 +614,15 @@ static bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// device-visible alias of a pinned (page-locked, mapped) HOST allocation, or NULL: kernels can then write results straight into
+// the caller's host buffer across PCIe instead of into a device staging buffer that is copied back afterwards
+static void *mapped_host_alias(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    return nullptr;
+}
+
 // pacfile.py:237-261
 static void build_header(PacCtx *ctx, int64_t nSamples, uint8_t *h) {
     auto le32 = [](uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; };
@@ -660,7 +654,13 @@ static int launch_analysis_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_analysis<T, LOGM>, (1 << LOGM) / 4, smem));
     if (perSM < 1) perSM = 1;
     int64_t grid = (int64_t)ctx->numSMs * perSM;
-    if (ctx->launchStream) grid = a.nwork;       // overlapped tiles (a persistent grid here measured 460 vs 354 ms: it never yields SMs): short-lived CTAs let the scan/pack kernels of the previous tile in
+    if (ctx->launchStream) {
+        // overlapped tiles: short-lived CTAs let the scan/pack kernels of the previous tile in (a persistent grid measured 460 vs
+        // 354 ms: it never yields SMs).  A few blocks per CTA amortise the per-thread table prologue (4 % of a one-block CTA).
+        static const int bpc = getenv("PAC_BLOCKS_PER_CTA") ? atoi(getenv("PAC_BLOCKS_PER_CTA")) : 4;
+        const int64_t g2 = (a.nwork + (bpc > 0 ? bpc : 1) - 1) / (bpc > 0 ? bpc : 1);
+        if (g2 > grid) grid = g2;
+    }
     if (grid > a.nwork) grid = a.nwork;
     if (grid < 1) grid = 1;
     { KTimer kt(ctx, PAC_K_ANALYSIS); k_analysis<T, LOGM><<<(unsigned)grid, (1 << LOGM) / 4, smem, LS(ctx)>>>(a); }
@@ -758,7 +758,12 @@ template <typename T>
 static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const int64_t *nSamples, int S, uint8_t *out,
                           int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace) {
     const int M = ctx->M, NB = ctx->bands.nBands, hdrB = header_bytes(ctx);
-    const bool pcmDev = is_device_ptr(pcm), outDev = is_device_ptr(out);
+    const bool pcmDev = is_device_ptr(pcm);
+    // out: device memory, or PINNED host memory (k_pack then writes every chunk straight into the caller's buffer while the next
+    // tile is analysed: no staging image, no copy-back phase at the end of a group, and only the outBytes[s] bytes of an image ever
+    // cross PCIe), else pageable host memory (staged group by group, below).  PAC_NO_MAPPED_OUT=1 forces the staged path.
+    uint8_t *outD = is_device_ptr(out) ? out : (getenv("PAC_NO_MAPPED_OUT") ? nullptr : reinterpret_cast<uint8_t *>(mapped_host_alias(out)));
+    const bool outDev = outD != nullptr;
     int64_t maxBlocksAll = 0;
     for (int s = 0; s < S; s++) {
         if (nSamples[s] < 0 || nSamples[s] > stride) FAIL(PAC_E_ARG, "nSamples[%d]=%lld outside [0, strideSamples]", s, (long long)nSamples[s]);
@@ -917,7 +922,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             if (g + 1 < nGroups) CK(h2d_group(g + 1));                                     // next group's copy overlaps this group's kernels
         }
         uint8_t *d_out;
-        if (outDev) d_out = out + (int64_t)s0 * cap;
+        if (outDev) d_out = outD + (int64_t)s0 * cap;
         else {
             d_out = ((g & 1) ? ctx->w_out2 : ctx->w_out).template as<uint8_t>();
             if (g >= 2) CK(cudaStreamWaitEvent(sB, ctx->evD[g & 1], 0));                  // its previous contents have been copied out

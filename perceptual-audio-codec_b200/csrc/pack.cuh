@@ -56,7 +56,7 @@ __device__ __forceinline__ void put_bits(unsigned *buf, unsigned pos, unsigned v
 template <typename T>
 __global__ void __launch_bounds__(kPackWarps * 32)
 k_pack(const PackArgs<T> a) {
-    __shared__ unsigned sbuf[kPackWarps][kChunkWords + 2];
+    __shared__ unsigned sbuf[kPackWarps][kChunkWords + 4];      // word 0: the '<L nBytes' prefix, payload from word 1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nchunks = (int64_t)a.S * a.nb * 2;
     const int NB = a.bands.nBands, M = a.M;
@@ -64,7 +64,7 @@ k_pack(const PackArgs<T> a) {
     const int largestScale = (1 << ec.nScaleBits) - 1;
     const int hdrBits = ec.nMantSizeBits + ec.nScaleBits;
     const int nGroups = M / 32;                          // M is 512 or 1024
-    unsigned *buf = sbuf[warp];
+    unsigned *buf = sbuf[warp] + 1;
     // static, lane = band: the band's first line and width
     const int loLane = lane < NB ? a.bands.lo[lane] : M;
     const int nlLane = lane < NB ? a.bands.lo[lane + 1] - a.bands.lo[lane] : 0;
@@ -162,24 +162,44 @@ k_pack(const PackArgs<T> a) {
             put_bits(buf, (unsigned)(fixedTotal + carry), __brev(a.lrms[w]) >> (32 - NB), NB);
         }
         __syncwarp();
-        // ---- store: [<L nBytes][payload] at the offset K4 assigned
+        // ---- store: [<L nBytes][payload] at the offset K4 assigned, as ONE byte stream out of shared memory (word -1 holds the
+        // length prefix, byte-swapped so that the big-endian stream reads as '<L'): unaligned head and tail bytewise, the body as
+        // 16-byte stores (512 contiguous bytes per warp instruction -- the output may be pinned HOST memory written across PCIe,
+        // where 32-byte transactions would waste the link)
         uint8_t *dst;
-        long long room;
-        if (a.perChunk) { dst = a.out + c * a.cap; room = a.cap; }
-        else {
-            long long off = a.chunkOff[c];
-            dst = a.out + (long long)s * a.cap + off;
-            room = a.cap - off;
-            if (room < 4 + (long long)nby) { if (lane == 0 && a.overflow) a.overflow[s] = 1; continue; }
-            if (lane < 4) dst[lane] = (uint8_t)(nby >> (8 * lane));               // '<L', pacfile.py:317
-            dst += 4;
+        const unsigned *src;
+        unsigned nout;
+        if (a.perChunk) {
+            dst = a.out + c * a.cap; src = buf; nout = nby;
+            if (a.cap < (long long)nby) { if (lane == 0 && a.overflow) a.overflow[s] = 1; continue; }
+        } else {
+            const long long off = a.chunkOff[c];
+            if (a.cap - off < 4 + (long long)nby) { if (lane == 0 && a.overflow) a.overflow[s] = 1; continue; }
+            dst = a.out + (long long)s * a.cap + off; src = buf - 1; nout = nby + 4;
+            if (lane == 0) buf[-1] = __byte_perm(nby, 0, 0x0123);                  // '<L', pacfile.py:317
             if (b == 0 && ch == 0) {                                              // WriteFileHeader, pacfile.py:237-261
                 uint8_t *h = a.out + (long long)s * a.cap;
                 for (int i = lane; i < a.headerBytes; i += 32) h[i] = a.header[(long long)s * a.headerBytes + i];
             }
+            __syncwarp();
         }
-        if (a.perChunk && room < (long long)nby) { if (lane == 0 && a.overflow) a.overflow[s] = 1; continue; }
-        for (unsigned i = lane; i < nby; i += 32) dst[i] = (uint8_t)(buf[i >> 2] >> (24 - 8 * (i & 3)));
+        auto byteAt = [&](unsigned i) { return (uint8_t)(src[i >> 2] >> (24 - 8 * (i & 3))); };
+        const unsigned head = min(nout, (unsigned)((16 - ((uintptr_t)dst & 15)) & 15));
+        if (lane < head) dst[lane] = byteAt(lane);
+        const unsigned nvec = (nout - head) >> 4;
+        const unsigned sh = 8 * (head & 3);
+        for (unsigned v = lane; v < nvec; v += 32) {
+            const unsigned wi = (head >> 2) + 4 * v;                               // first source word of this 16-byte group
+            const unsigned w0 = src[wi], w1 = src[wi + 1], w2 = src[wi + 2], w3 = src[wi + 3], w4 = src[wi + 4];
+            uint4 o;
+            o.x = __byte_perm(__funnelshift_l(w1, w0, sh), 0, 0x0123);
+            o.y = __byte_perm(__funnelshift_l(w2, w1, sh), 0, 0x0123);
+            o.z = __byte_perm(__funnelshift_l(w3, w2, sh), 0, 0x0123);
+            o.w = __byte_perm(__funnelshift_l(w4, w3, sh), 0, 0x0123);
+            *reinterpret_cast<uint4 *>(dst + head + 16 * v) = o;
+        }
+        const unsigned done = head + 16 * nvec;
+        if (done + lane < nout) dst[done + lane] = byteAt(done + lane);
         __syncwarp();
     }
 }

@@ -141,12 +141,13 @@ def analysis(T, xl, xr, nLines):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# v2 threshold evaluation used by the fp32 fast mode (csrc/analysis.cuh: masked_curve_fast).
+# Scan-based threshold evaluation used by the fp32 fast mode (csrc/analysis.cuh: masked_curve_fast).
 #
 # The reference sums, for every masker, an exp over all 1024 lines (O(maskers x lines)).  The spreading function is
 # piecewise: plateau (|dz| <= .5 Bark), lower skirt (fixed -27 dB/Bark) and upper skirt (-27 + .367 max(P-40, 0)
-# dB/Bark).  Fixed-slope parts are separable, so they become weighted scans over the lines with STATIC weights;
-# only the upper skirts of maskers louder than 40 dB keep a pairwise evaluation, and only over the lines above them.
+# dB/Bark).  Fixed-slope parts are separable, so they become weighted scans with STATIC weights (curve_v3 below: over the
+# bins); only the upper skirts of maskers louder than 40 dB keep a pairwise evaluation, over the lines above them, and
+# culled per 64-line half-chunk.
 # ---------------------------------------------------------------------------------------------------------------
 
 K10 = np.log2(10.0) / 10.0
@@ -184,8 +185,8 @@ class Geometry:
 
 
 def weighted_suffix_scan(U, z, dn, dtype):
-    """L[i] = sum_{j>=i} U[j] 2^{dn (z_j - z_i)} evaluated the way the kernel does: 4 lines per thread, warp
-    Kogge-Stone with static weights, block carry."""
+    """L[i] = sum_{j>=i} U[j] 2^{dn (z_j - z_i)} evaluated the way the kernel does: 4 entries per thread, warp
+    Kogge-Stone with static weights, block carry (z = the Bark positions of the scan's domain: the bins for curve_v3)."""
     M = len(U)
     w = lambda i, j: dtype(2.0 ** (dn * (z[j] - z[i])))
     a = np.zeros(M, dtype)
@@ -225,12 +226,22 @@ def weighted_suffix_scan(U, z, dn, dtype):
     return out
 
 
-def curve_v2(T, G, F, drop, dtype=np.float32, stats=None):
+# ---------------------------------------------------------------------------------------------------------------
+# curve_v3: the fixed-slope skirts as scans over the BINS (round 1 scanned over the lines, gathering up to three bins per line).  A masker at bin k spreads downwards as
+# A_k 2^{dn (zp_k - .5 - z_i)} over the lines i <= eL[k].  With pb(i) = first bin whose lower skirt reaches line i (the same index
+# that bounds the plateau window [pa, pb)), the sum over maskers factorises:
+#     low(i) = SD[pb(i)] * 2^{dn (zp_pb - .5 - z_i)},   SD[k] = sum_{k' >= k} A_k' 2^{dn (zp_k' - zp_k)}   (a scan over bins)
+# and likewise the quiet upper skirts, up(i) = SA[pa(i) - 1] * 2^{dn (z_i - zp_{pa-1} - .5)}, SA an ascending scan over the quiet
+# maskers.  The scans run on the values the peak-picking thread already holds (no dense injection arrays, no per-line gathers of
+# up to three bins, no per-masker entry exponentials); a line needs one entry of each scan and a static factor <= 1.
+# ---------------------------------------------------------------------------------------------------------------
+
+def curve_v3(T, G, F, drop, dtype=np.float32, stats=None):
     M, N = T.M, T.N
     P = (F.real.astype(dtype) ** 2 + F.imag.astype(dtype) ** 2)[:M]
     k = np.arange(1, M - 1)
     pk = k[(P[k] > P[k - 1]) & (P[k] > P[k + 1]) & (P[k] > dtype(1e-6))]
-    A = np.zeros(M, dtype); V = np.zeros(M, dtype); W = np.zeros(M, dtype)
+    A = np.zeros(M, dtype); Aq = np.zeros(M, dtype)
     loud = []
     cn = dtype(8.0 / 3.0 * 4.0 / N ** 2)
     for kk in pk:
@@ -238,35 +249,45 @@ def curve_v2(T, G, F, drop, dtype=np.float32, stats=None):
         Pm = dtype(max(96 + 10 * np.log10(max(dtype(cn * s), dtype(10 ** -12.6))), -30.0))
         c0 = dtype((Pm - dtype(drop) - dtype(96)) * dtype(K10))
         A[kk] = dtype(2.0 ** c0)
-        if G.eL[kk] >= 0:
-            V[kk] = dtype(2.0 ** dtype(c0 + dtype(G.dn) * dtype(G.gL[kk])))
         lev = dtype(0.367) * max(Pm - dtype(40), dtype(0))
-        if G.eU[kk] < M:
-            if lev > 0:
+        if lev > 0:
+            if G.eU[kk] < M:
                 loud.append((kk, c0, dtype((lev - dtype(27)) * dtype(K10))))
-            else:
-                W[kk] = dtype(2.0 ** dtype(c0 + dtype(G.dn) * dtype(G.gU[kk])))
-    # injections gathered per line (deterministic order)
-    UL = np.array([np.sum(V[G.kLa[i]:G.kLb[i]], dtype=dtype) for i in range(M)], dtype)
-    UU = np.array([np.sum(W[G.kUa[i]:G.kUb[i]], dtype=dtype) for i in range(M)], dtype)
-    low = weighted_suffix_scan(UL, T.zline, G.dn, dtype)
-    upq = weighted_suffix_scan(UU[::-1].copy(), -T.zline[::-1], G.dn, dtype)[::-1]
-    plat = np.array([np.sum(A[G.pa[i]:G.pb[i]], dtype=dtype) for i in range(M)], dtype)
-    acc = (low + plat + upq).astype(dtype)
-    # loud upper skirts: pairwise over the lines above the masker
-    zl = T.zline
-    npairs = 0
+        else:
+            Aq[kk] = A[kk]
+    zp, zl = T.zpeak, T.zline
+    SD = weighted_suffix_scan(A, zp, G.dn, dtype)                                  # SD[k] = sum_{k' >= k} A 2^{dn (zp_k' - zp_k)}
+    SA = weighted_suffix_scan(Aq[::-1].copy(), -zp[::-1], G.dn, dtype)[::-1]        # SA[k] = sum_{k' <= k} Aq 2^{dn (zp_k - zp_k')}
+    SDx = np.concatenate([SD, [dtype(0)]])                                          # SD[M] = 0
+    SAx = np.concatenate([[dtype(0)], SA])                                          # SA[-1] = 0 (index shifted by one)
+    pa, pb = G.pa, G.pb
+    fL = np.where(pb < M, 2.0 ** (G.dn * (zp[np.minimum(pb, M - 1)] - 0.5 - zl)), 0.0).astype(dtype)
+    fU = np.where(pa > 0, 2.0 ** (G.dn * (zl - zp[np.maximum(pa - 1, 0)] - 0.5)), 0.0).astype(dtype)
+    assert fL.max() <= 1.0 and fU.max() <= 1.0
+    Sp = np.concatenate([[0.0], np.cumsum(A.astype(np.float64))])                   # double prefix (plateau = exact range sums)
+    plat = (Sp[pb] - Sp[pa]).astype(dtype)
+    acc = (((SDx[pb] * fL).astype(dtype) + (SAx[pa] * fU).astype(dtype)).astype(dtype) + plat).astype(dtype)
+    acc = (acc + T.tiq.astype(dtype)).astype(dtype)
+    npairs = nculled = 0
+    part = acc.copy()
     for kk, c0, up in loud:
         i0 = G.eU[kk]
-        # the kernel forms B = c0 - up/2 - up * z_masker once per masker in double (split hi + lo) and evaluates the exponent at
-        # line i as fma(up, z_i.hi, B.hi) + fma(up, z_i.lo, B.lo): the double expression below rounded once
         B = np.float64(c0) - 0.5 * np.float64(up) - np.float64(up) * T.zpeak[kk]
-        e = (np.float64(up) * zl[i0:] + B).astype(dtype)
-        acc[i0:] += (2.0 ** e.astype(np.float64)).astype(dtype)
-        npairs += M - i0
+        for h in range(M // 64):
+            lo, hi = 64 * h, 64 * h + 64
+            if i0 >= hi:
+                continue
+            cut = np.log2(np.float64(part[lo:hi].min())) - 30.01
+            if dtype(np.float64(up) * dtype(zl[lo]) + dtype(B)) < cut:
+                nculled += hi - max(lo, i0)
+                continue
+            a = max(lo, i0)
+            e = (np.float64(up) * zl[a:hi] + B).astype(dtype)
+            acc[a:hi] += (2.0 ** e.astype(np.float64)).astype(dtype)
+            npairs += hi - a
     if stats is not None:
         stats["peaks"] = stats.get("peaks", 0) + len(pk)
         stats["loud"] = stats.get("loud", 0) + len(loud)
         stats["pairs"] = stats.get("pairs", 0) + npairs
-    tot = (acc + T.tiq.astype(dtype)).astype(dtype)
-    return np.maximum(dtype(96) + dtype(10) * np.log10(np.maximum(tot, dtype(10 ** -12.6))).astype(dtype), dtype(-30))
+        stats["culled"] = stats.get("culled", 0) + nculled
+    return np.maximum(dtype(96) + dtype(10) * np.log10(np.maximum(acc, dtype(10 ** -12.6))).astype(dtype), dtype(-30))

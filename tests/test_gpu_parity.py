@@ -673,6 +673,27 @@ def test_device_input_produced_on_torchs_default_stream_without_sync(pb, oracle)
     e.close()
 
 
+def test_pinned_host_output_is_written_in_place(pb, oracle):
+    """out in PINNED host memory: k_pack writes every chunk straight into the caller's buffer (mapped across PCIe), no staging image
+    and no copy-back; the images equal the staged path's (pageable numpy out) and the oracle's, for ragged lengths too, and bytes
+    beyond outBytes[s] are left untouched (the staged copy used to overwrite them with stale data)."""
+    import torch
+    e = pb.Engine(0, "fp64")
+    n = 30 * 1024 + 333
+    pcm = np.stack([synth_pcm(31, n), synth_pcm(32, n, "left"), synth_pcm(33, n, "silence")])
+    ns = np.array([n, n - 5000, 777], np.int64)
+    cap = e.encode_bound(n)
+    out_p = torch.full((3, cap), 0xAB, dtype=torch.uint8).pin_memory()
+    pcm_p = torch.from_numpy(pcm).pin_memory()
+    _, ob = e.encode_batch(pcm_p.numpy(), nSamples=ns, out=out_p.numpy(), cap=cap)
+    want = e.encode_batch(pcm, nSamples=ns)                      # pageable in, pageable out: the staged path
+    for s in range(3):
+        img = out_p.numpy()[s]
+        assert img[:ob[s]].tobytes() == want[s] == oracle.encode_stream(pcm[s, :ns[s]])[0], s
+        assert np.all(img[ob[s]:] == 0xAB), s
+    e.close()
+
+
 def test_output_capacity_error(e64):
     pcm = synth_pcm(1, 20000)
     with pytest.raises(Exception) as ei:

@@ -39,11 +39,10 @@ def test_model_matches_reference_stage_dumps(stages):
 
 
 def test_scan_based_curve_matches_direct_evaluation(stages):
-    """fp32 fast path (csrc/analysis.cuh:masked_curve_fast): scans for the fixed-slope skirts, prefix-sum plateau,
+    """fp32 fast path (csrc/analysis.cuh:masked_curve_fast): scans over the bins for the fixed-slope skirts, prefix-sum plateau,
     pairwise upper skirts only for maskers above 40 dB.  Against the direct masker x line evaluation
     (psychoac.py:431-456) in float64: tolerance 1e-4 dB = the 1e-5 * max(|SMR|, 10 dB) budget of north_star.
-    (A further cut-off of loud skirts 81 dB below the threshold in quiet was tried: 72 % fewer pairs, same error, but no
-    measurable gain on the B200 -- the kernel is latency- not issue-bound -- so it is not in the product.)"""
+    The loud skirts are culled per 64-line half-chunk as in the kernel (30 bits below the half-chunk's smallest partial threshold)."""
     T = ma.Tables()
     G = ma.Geometry(T)
     worst, stats = 0.0, {}
@@ -53,7 +52,7 @@ def test_scan_based_curve_matches_direct_evaluation(stages):
         for sig, drop in ((x[:, 0], 15.0), (0.5 * (x[:, 0] - x[:, 1]), 0.0)):
             F = np.fft.fft(sig * T.sine * T.hann)[:T.M + 1]
             ref = ma.curve(T, F, drop)
-            got = ma.curve_v2(T, G, F, drop, dtype=np.float32, stats=stats)
+            got = ma.curve_v3(T, G, F, drop, dtype=np.float32, stats=stats)
             worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - ref))))
     print("worst |dB error|", worst, stats)
     assert worst <= 1e-4
