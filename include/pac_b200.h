@@ -16,6 +16,7 @@
  */
 #ifndef PAC_B200_H
 #define PAC_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,6 +109,12 @@ int pac_set_stream(PacCtx *ctx, void *stream);
 #define PAC_NKINDS     8
 int pac_timing_enable(PacCtx *ctx, int on);                       /* also resets the accumulators */
 int pac_timing_get(PacCtx *ctx, double *ms /*[PAC_NKINDS]*/, int64_t *count /*[PAC_NKINDS]*/);
+
+/* Page-locked, device-mapped host memory for the whole-stream calls' host buffers (cudaHostAlloc): PCM slabs read straight from
+ * WAV files are copied by DMA without a pageable bounce, and a pinned `out` is written by the pack kernel in place (see
+ * pac_encode_batch).  NULL on failure.  Not tied to a context; free with pac_pinned_free. */
+void *pac_pinned_alloc(size_t nbytes);
+void  pac_pinned_free(void *p);
 
 /* ------------------------------------------------------------------ whole streams (the hot path) */
 /* ceil(n/nMDCTLines)+1: pcmfile.py:66-82 + the flush block of pacfile.py:355-365 */

@@ -70,6 +70,10 @@ def lib():
     L.pac_last_error.argtypes = [vp]
     L.pac_last_error.restype = C.c_char_p
     L.pac_version.restype = C.c_char_p
+    L.pac_pinned_alloc.argtypes = [C.c_size_t]
+    L.pac_pinned_alloc.restype = vp
+    L.pac_pinned_free.argtypes = [vp]
+    L.pac_pinned_free.restype = None
     L.pac_band_layout.argtypes = [vp, i32p, i32p]
     L.pac_launch_count.argtypes = [vp]
     L.pac_launch_count.restype = C.c_int64
@@ -190,6 +194,34 @@ def _vp(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(a.ctypes.data)
+
+
+class _PinnedBlock(object):
+    """owner of one pac_pinned_alloc allocation (freed when the last numpy view dies)"""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().pac_pinned_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("pac_pinned_alloc(%d) failed" % self.nbytes)
+        self.__array_interface__ = {"shape": (max(self.nbytes, 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().pac_pinned_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array in page-locked, device-mapped host memory (pac_pinned_alloc): the buffers of encode_batch / decode_batch then move
+    by DMA, and a pinned `out` of encode_batch is written in place by the pack kernel."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(n)
+    return np.asarray(blk)[:n].view(dt).reshape(shape)          # the view keeps blk alive through its base chain
 
 
 class Engine(object):

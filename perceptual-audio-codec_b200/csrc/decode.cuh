@@ -217,7 +217,11 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a
             BitReader sr = r;                                         // nLines sign bits first (:202-204) ...
             r.seek(p, r.used + (hi - lo));                            // ... then the codes
             const uint32_t signBit = 1u << (ba - 1);
-            for (int i = lo; i < hi; i++) {
+            uint32_t sbits = 0;                                       // up to 32 buffered sign bits, next one in bit 31
+            int sleft = 0;
+            int i = lo;
+            while (i < hi) {
+                if (sleft == 0) { const int n = min(32, hi - i); sbits = sr.get(n) << (32 - n); sleft = n; }
                 uint32_t e = lut[r.peek(kLutBits)];
                 int sym;
                 if (e & kLutLeaf) { r.skip((int)(e & 0xff)); sym = (int)((e >> 8) & 0x7fffff) - 1; }
@@ -233,11 +237,14 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a
                     sym = a.dt.sym[node];
                 }
                 uint32_t m = sym < 0 ? r.get(ba) : (uint32_t)sym;     // escape: Huffman.py:326-327
-                if (sr.get(1)) m += signBit;                          // pacfile.py:210
+                if (sbits >> 31) m += signBit;                        // pacfile.py:210
+                sbits <<= 1; sleft--;
                 if (m > 0xffffu) { bad = true; break; }               // no ba <= 16 code is that large
                 if (a.o_mant) a.o_mant[c * M + i] = (int32_t)m;
                 if (sink.row) sink.push(m, i);
+                i++;
             }
+            if (bad) break;
         }
         uint32_t lr = 0;
         for (int bd = 0; bd < NB; bd++) lr |= r.get(1) << bd;         // :216-217

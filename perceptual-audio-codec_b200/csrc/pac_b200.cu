@@ -585,6 +585,13 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     delete ctx;
 }
 
+extern "C" void *pac_pinned_alloc(size_t nbytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void pac_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int pac_band_layout(PacCtx *ctx, int32_t *nLines, int32_t *nBands) {
     if (!ctx || !nLines || !nBands) return PAC_E_ARG;
     for (int b = 0; b < ctx->bands.nBands; b++) nLines[b] = ctx->nLines[b];

@@ -694,6 +694,38 @@ def test_pinned_host_output_is_written_in_place(pb, oracle):
     e.close()
 
 
+def test_batched_wav_ingest_and_egress(gold_dir, manifest, tmp_path):
+    """pacb200_batch.encode_files / decode_files (the batched form of PCMFile.ReadFileHeader/ReadDataBlock + PACFile.WriteDataBlock
+    and back, pcmfile.py:32-147): WAV files are read straight into one pinned slab, the .pac images are written from the pinned
+    output buffer, and the decoder's WAV files from the pinned PCM buffer -- byte-identical to the reference's files; a WAV whose
+    'data' chunk promises more samples than the file holds is zero-filled like PCMFile.ReadDataBlock does (pcmfile.py:77-79)."""
+    import pacb200_batch as pbat
+    names = ["piano_test2", "castanets"]
+    wavs = [os.path.join(gold_dir, n + ".wav") for n in names]
+    paks = [str(tmp_path / (n + ".wak")) for n in names]
+    sizes = pbat.encode_files(wavs, precision="fp64", out_paths=paks)
+    for n, pth, sz in zip(names, paks, sizes):
+        data = open(pth, "rb").read()
+        assert len(data) == sz == manifest["files"][n]["pac_bytes"] and sha(data) == manifest["files"][n]["pac_sha256"], n
+    as_bytes = pbat.encode_files(wavs, precision="fp64")
+    assert [sha(b) for b in as_bytes] == [manifest["files"][n]["pac_sha256"] for n in names]
+    outs = [str(tmp_path / (n + ".out.wav")) for n in names]
+    pbat.decode_files(paks, precision="fp64", out_paths=outs)
+    for n, pth in zip(names, outs):
+        assert sha(open(pth, "rb").read()) == manifest["files"][n]["out_sha256"], n
+    assert [sha(w) for w in pbat.decode_files(as_bytes, precision="fp64")] == [manifest["files"][n]["out_sha256"] for n in names]
+    # truncated file: header says n samples, fewer are present
+    rate, pcm = pbat.read_wav(wavs[0])
+    full = pbat.wav_bytes(pcm[:30000], rate, 30000)
+    cut = tmp_path / "cut.wav"
+    cut.write_bytes(full[:44 + 4 * 20001 + 2])                 # 20001 whole frames and half a frame
+    ref = pcm[:30000].copy(); ref[20001:] = 0; ref[20001, 0] = pcm[20001, 0]     # the half frame's bytes are kept, as the reference does
+    want = pbat.encode_files([str(cut)], precision="fp64")[0]
+    whole = tmp_path / "whole.wav"
+    whole.write_bytes(pbat.wav_bytes(ref, rate, 30000))
+    assert want == pbat.encode_files([str(whole)], precision="fp64")[0]
+
+
 def test_output_capacity_error(e64):
     pcm = synth_pcm(1, 20000)
     with pytest.raises(Exception) as ei:
