@@ -85,15 +85,13 @@ __device__ __forceinline__ void fft_dif(typename Vec2<T>::type *buf, int nbatch,
 //   pass 1: elements j + 64 r            (j < 64)            twiddle W_1024^(j p)
 //   pass 2: elements 64 g + j + 4 r      (g < 16, j < 4)     twiddle W_64^(j p)
 //   pass 3: radix 4 on 4 consecutive elements, no twiddle
-// Frequency k = p1 + 16 p2 + 256 p3 ends at position 64 p1 + 4 p2 + p3 (fft_pos1024 below).  With the padded layout
-// (one spare element per 16) every pass is conflict-free for 64-bit accesses.
+// The last pass writes frequency k = p1 + 16 p2 + 256 p3 (which its in-place form would leave at 64 p1 + 4 p2 + p3) to its
+// natural position.  With the padded layout (one spare element per 16) every pass is conflict-free for 64-bit accesses.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int fft_pos1024(int k) { return ((k & 15) << 6) | (((k >> 4) & 15) << 2) | (k >> 8); }
-
-// frequency k of the fp32 batch FFTs (1024-point: register-blocked order; otherwise the radix-4 order)
+// position of frequency k: the register-blocked 1024-point FFT leaves natural order, the radix-4 one digit-reversed order
 template <int LOGN, bool R16>
 __device__ __forceinline__ int fft_pos_sel(int k) {
-    if constexpr (R16 && LOGN == 10) return fft_pos1024(k);
+    if constexpr (R16 && LOGN == 10) return k;
     else return fft_pos<LOGN>(k);
 }
 
@@ -164,13 +162,35 @@ __device__ __forceinline__ void fft1024_r16(float2 *buf, int nbatch, int bstride
             }
     }
     __syncthreads();
-    // ---- pass 3: radix 4 on consecutive elements
-    for (int w = tid; w < nbatch * 256; w += NTHREADS) {
-        const int bt = w >> 8, g = w & 255;
-        float2 *p = buf + bt * bstride + fft_pad<PAD>(4 * g);  // 4 g .. 4 g + 3 never straddle a pad (16 | 4 g + 4 only at the end)
-        float2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
-        radix4_f(a0, a1, a2, a3);
-        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+    // ---- pass 3: radix 4 on consecutive elements, AUTOSORTED: frequency k = p1 + 16 p2 + 256 p3 sits at position 64 p1 + 4 p2 + p3;
+    // every thread keeps its groups in registers across a barrier and writes them to their natural places (lanes -> k stride 16
+    // -> 17 padded elements: conflict-free), so the readers index by k directly -- no digit-reversed gathers (which cost 4-way bank
+    // conflicts on every spectrum read, ncu) and no index arithmetic
+    // (two groups per thread are in flight across each barrier: writes of one transform only collide with reads of the same one)
+    for (int w0 = 0; w0 < nbatch * 256; w0 += 2 * NTHREADS) {
+        float2 y[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int w = w0 + tid + i * NTHREADS;
+            if (w < nbatch * 256) {
+                const int bt = w >> 8, g = w & 255;
+                const float2 *p = buf + bt * bstride + fft_pad<PAD>(4 * g);
+                y[i][0] = p[0]; y[i][1] = p[1]; y[i][2] = p[2]; y[i][3] = p[3];
+                radix4_f(y[i][0], y[i][1], y[i][2], y[i][3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int w = w0 + tid + i * NTHREADS;
+            if (w < nbatch * 256) {
+                const int bt = w >> 8, g = w & 255;
+                float2 *p = buf + bt * bstride;
+                const int kb = (g >> 4) + 16 * (g & 15);
+#pragma unroll
+                for (int p3 = 0; p3 < 4; p3++) p[fft_pad<PAD>(kb + 256 * p3)] = y[i][p3];
+            }
+        }
     }
     __syncthreads();
 }
