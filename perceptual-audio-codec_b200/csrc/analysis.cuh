@@ -21,6 +21,12 @@
 
 namespace pac {
 
+__device__ __forceinline__ void cp_async16_a(void *smemDst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_a() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_a() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename T>
 struct AnalysisArgs {
     // ---- input: exactly one of pcm / blocks
@@ -31,7 +37,8 @@ struct AnalysisArgs {
     int S, b0, nb;               // work item w: stream s = w / nb, block b = b0 + w % nb
     int64_t nwork;
     int nScaleBits;
-    // ---- outputs, indexed by w
+    // ---- outputs, indexed by w.  fp32 mode: lines / oscale are ALSO inputs -- k_mdct (mdct.cuh) has left the scaled L/R lines and
+    //      the overall scales there; the lines are overwritten in place with the LRMS-selected ones
     T *lines;                    // [nwork][2][M]  LRMS-selected scaled lines
     T *smr;                      // [nwork][2][kMaxBands]
     T *bmax;                     // [nwork][2][kMaxBands] max |selected line| per band
@@ -544,7 +551,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 __syncthreads();
             }
             T mx[2] = {0, 0};
-            if constexpr (sizeof(T) == 8) {
+            {
                 for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
                     int ch = e / H, n = e - ch * H;
                     const T *x = xt + ch * XS;
@@ -564,44 +571,6 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                     T m = fmax(fabs(v0), fabs(v1));
                     if (ch == 0) mx[0] = fmax(mx[0], m); else mx[1] = fmax(mx[1], m);
                 }
-            } else {
-                // fp32 mode: an fp32 FFT leaves an error floor of ~1e-7 x (largest line) on EVERY line, i.e. far more than
-                // 1e-5 relative on the weak high-frequency lines.  The MDCT is ~1% of the block's work, so it is done in
-                // fp64 (fold, twiddles, butterflies) and only then rounded to fp32.
-                double2 *Wd = reinterpret_cast<double2 *>(&sm.W[0][0]);       // [2][H] double2 = 16 KB <= sizeof(W)
-                const DevTables<double> &td = a.tabd;
-                // PCM input: the exact int16 code is recovered from the float sample in shared memory (|code| <= 32767 fits a
-                // float exactly) and widened, so the fold sees the same doubles as the fp64 mode without a second trip to
-                // global memory.  Per-block API (arbitrary doubles): re-read them.
-                const DevTables<double> &tdd = a.tabd;
-                auto xd = [&](int ch, int n) -> double {
-                    double v;
-                    if (a.pcm) v = (double)__float2int_rn(xt[ch * XS + XI(n)] * 32767.5f) * (2.0 / 65535.0);
-                    else v = a.blocks[w * 2 * N + ch * N + n];
-                    return v * tdd.sinw[n];
-                };
-                for (int e = tid; e < 2 * H; e += NT) {
-                    int ch = e / H, n = e - ch * H;
-                    int m0 = 2 * n, m1 = M - 1 - 2 * n;
-                    double u0 = m0 < H ? -xd(ch, 3 * H - 1 - m0) - xd(ch, 3 * H + m0) : xd(ch, m0 - H) - xd(ch, 2 * H - 1 - (m0 - H));
-                    double u1 = m1 < H ? -xd(ch, 3 * H - 1 - m1) - xd(ch, 3 * H + m1) : xd(ch, m1 - H) - xd(ch, 2 * H - 1 - (m1 - H));
-                    Wd[ch * H + n] = cmul(mk2<double>(u0, u1), td.mdct_pre[n]);
-                }
-                __syncthreads();
-                fft_dif<double, LOGM - 1, NT>(Wd, 2, H, td.tw, 2);
-                double mxd[2] = {0, 0};
-                for (int e = tid; e < 2 * H; e += NT) {
-                    int ch = e / H, k = e - ch * H;
-                    double2 y = cmul(Wd[ch * H + fft_pos<LOGM - 1>(k)], td.mdct_post[k]);
-                    double v0 = (2.0 / (double)N) * y.x, v1 = -(2.0 / (double)N) * y.y;
-                    // kept in fp32 up to the power-of-two overall scale: rounding to fp32 commutes with that scaling
-                    sm.Lb[ch][2 * k] = (T)v0;
-                    sm.Lb[ch][M - 1 - 2 * k] = (T)v1;
-                    double m = fmax(fabs(v0), fabs(v1));
-                    if (ch == 0) mxd[0] = fmax(mxd[0], m); else mxd[1] = fmax(mxd[1], m);
-                }
-                mx[0] = (T)mxd[0]; mx[1] = (T)mxd[1];
-                // the overall scale only needs max|line|; its fp32 rounding can move the quantiser boundary by 6e-8 relative
             }
             mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
             if (lane == 0) { sm.red[warp] = mx[0]; sm.red[32 + warp] = mx[1]; }
@@ -618,7 +587,16 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 sm.Lb[ch][i] *= (T)(1 << (ch ? osc1 : osc0));      // codec.py:246
             }
         };
-        if constexpr (FAST || MDCT_ONLY) sectionC();   // fp32: MDCT first, while x is still in shared memory (the FFT batch below runs in place)
+        if constexpr (FAST) {
+            // fp32 mode: window + MDCT + overall scale ran as their own fp64 kernel (mdct.cuh: k_mdct) and left the scaled L/R lines in
+            // a.lines and the scales in a.oscale.  The lines travel into Lb by cp.async while the spectra and the six curves are
+            // computed (section F is their first reader, and overwrites a.lines in place with the LRMS-selected lines).
+            const T *src = a.lines + w * 2 * M;
+            for (int e = tid; e < 2 * M / 4; e += NT) cp_async16_a(&sm.Lb[0][0] + 4 * e, src + 4 * e);
+            cp_async_commit_a();
+            osc0 = a.oscale[w * 2]; osc1 = a.oscale[w * 2 + 1];
+        }
+        if constexpr (MDCT_ONLY) sectionC();
         if constexpr (MDCT_ONLY) {
             __syncthreads();
             for (int e = tid; e < 2 * M; e += NT) a.lines[w * 2 * M + e] = sm.Lb[e / M][e % M];
@@ -736,6 +714,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[5]);   // :562
         }
         // ------------------------------------------------ F. SMR candidates, band maxima, select
+        if constexpr (FAST) { cp_async_wait_a(); __syncthreads(); }       // the L/R lines have landed in Lb
         const uint32_t lrms = sm.lrms;
         T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
         T outl[2][4];

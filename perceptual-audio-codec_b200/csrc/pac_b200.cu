@@ -13,6 +13,7 @@
 #include "analysis.cuh"
 #include "common.cuh"
 #include "decode.cuh"
+#include "mdct.cuh"
 #include "pack.cuh"
 #include "scan.cuh"
 #include "stages.cuh"
@@ -100,8 +101,7 @@ struct PacCtx {
     // Huffman
     unsigned long long *lenLut = nullptr;
     ulonglong4 *lenLut4 = nullptr;
-    uint32_t *codeFlat = nullptr;
-    uint8_t *lenFlat = nullptr;
+    uint32_t *codeLen = nullptr;
     uint32_t *decLut = nullptr;
     int32_t *trieChild = nullptr, *trieSym = nullptr;
     DecodeTables dt{};
@@ -433,10 +433,16 @@ static int build_huffman(PacCtx *ctx, const PacHuffTables *h) {
     }
     CK(cudaMalloc(&ctx->lenLut, lut.size() * 8));
     CK(cudaMemcpy(ctx->lenLut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->codeFlat, (size_t)total * 4));
-    CK(cudaMemcpy(ctx->codeFlat, h->code, (size_t)total * 4, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->lenFlat, (size_t)total));
-    CK(cudaMemcpy(ctx->lenFlat, h->len, (size_t)total, cudaMemcpyHostToDevice));
+    {   // the pack kernel's table: code << 5 | length in one word (codes are at most 26 bits: build_huffman rejects lengths > 31, and a
+        // code longer than 27 bits could not share the word)
+        std::vector<uint32_t> cl((size_t)total);
+        for (int i = 0; i < total; i++) {
+            if (h->len[i] > 27) FAIL(PAC_E_ARG, "Huffman code longer than 27 bits");
+            cl[i] = (h->code[i] << 5) | h->len[i];
+        }
+        CK(cudaMalloc(&ctx->codeLen, (size_t)total * 4));
+        CK(cudaMemcpy(ctx->codeLen, cl.data(), (size_t)total * 4, cudaMemcpyHostToDevice));
+    }
     // decoder: binary tries (Huffman.py:321-344 does a string-prefix search; a trie is the same relation)
     HostTrie tr;
     int root[kNTables];
@@ -575,7 +581,7 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     for (auto &kv : ctx->td) cudaFree(kv.second.mem);
     for (auto &kv : ctx->winTables) cudaFree(kv.second);
     for (auto &kv : ctx->fastTables) cudaFree(kv.second.second);
-    cudaFree(ctx->lenLut); cudaFree(ctx->lenLut4); cudaFree(ctx->codeFlat); cudaFree(ctx->lenFlat);
+    cudaFree(ctx->lenLut); cudaFree(ctx->lenLut4); cudaFree(ctx->codeLen);
     cudaFree(ctx->decLut); cudaFree(ctx->trieChild); cudaFree(ctx->trieSym);
     DBuf *bufs[] = {&ctx->w_pcm, &ctx->w_out, &ctx->w_ns, &ctx->w_state, &ctx->w_lines, &ctx->w_smr, &ctx->w_bmax, &ctx->w_osc,
                     &ctx->w_lrms, &ctx->w_ba, &ctx->w_sf, &ctx->w_tid, &ctx->w_nby, &ctx->w_coff, &ctx->w_trE, &ctx->w_trD,
@@ -695,8 +701,39 @@ static int launch_mdct_only_t(PacCtx *ctx, AnalysisArgs<T> &a) {
     return PAC_OK;
 }
 
+// K1 of the fp32 fast mode: window + MDCT + overall scale as their own fp64 kernel (mdct.cuh), one CTA per stereo block
+template <int LOGM>
+static int launch_mdct_t(PacCtx *ctx, const MdctArgs &m) {
+    const size_t smem = sizeof(EncMdctSmem<LOGM>);
+    CK(cudaFuncSetAttribute(k_mdct_enc<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)ctx->numSMs * 32;
+    if (grid > m.nwork) grid = m.nwork;
+    if (grid < 1) grid = 1;
+    { KTimer kt(ctx, PAC_K_MDCT); k_mdct_enc<LOGM><<<(unsigned)grid, (1 << LOGM) / 8, smem, LS(ctx)>>>(m); }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PAC_OK;
+}
+
+static int launch_mdct(PacCtx *ctx, const AnalysisArgs<float> &a) {
+    MdctArgs m{};
+    m.pcm = a.pcm; m.strideSamples = a.strideSamples; m.nSamples = a.nSamples; m.blocks = a.blocks;
+    m.S = a.S; m.b0 = a.b0; m.nb = a.nb; m.nwork = a.nwork; m.nScaleBits = ctx->p.nScaleBits;
+    m.lines = a.lines; m.oscale = a.oscale;
+    int rc = get_tables<double>(ctx, ctx->N, &m.tabd);
+    if (rc) return rc;
+    if (ctx->LOGM == 10) return launch_mdct_t<10>(ctx, m);
+    if (ctx->LOGM == 9) return launch_mdct_t<9>(ctx, m);
+    FAIL(PAC_E_ARG, "unsupported nMDCTLines");
+}
+static int launch_mdct(PacCtx *, const AnalysisArgs<double> &) { return PAC_OK; }     // fp64 mode: the MDCT is a section of k_analysis
+
 template <typename T>
 static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
+    {   // fp32 mode: k_mdct first, on the same stream; k_analysis picks its lines and scales up from a.lines / a.oscale
+        int rcm = launch_mdct(ctx, a);
+        if (rcm) return rcm;
+    }
     a.bands = ctx->bands;
     a.nScaleBits = ctx->p.nScaleBits;
     int rc = get_tables<T>(ctx, ctx->N, &a.tab);
@@ -735,7 +772,7 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
 
 template <typename T>
 static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
-    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.codeLut = ctx->codeFlat; a.lenLutFlat = ctx->lenFlat;
+    a.ec = ctx->ec; a.bands = ctx->bands; a.M = ctx->M; a.codeLen = ctx->codeLen;
     {
         DevTables<T> tb;
         int rc = get_tables<T>(ctx, ctx->N, &tb);
@@ -1302,9 +1339,10 @@ static int mdct_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const i
         if ((rc = get_tables<double>(ctx, ctx->N, &aa.tabd))) return rc;
         if (full) { aa.smr = ctx->w_smr.as<T>(); aa.bmax = ctx->w_bmax.as<T>(); aa.lrms = ctx->w_lrms.as<uint32_t>(); }
         CK(cudaEventRecord(e0, ctx->stream));
-        if (full) rc = launch_analysis<T>(ctx, aa);           // the whole analysis kernel, by itself (persistent grid)
-        else if (ctx->LOGM == 10) rc = launch_mdct_only_t<T, 10>(ctx, aa);
-        else rc = launch_mdct_only_t<T, 9>(ctx, aa);
+        if (full) rc = launch_analysis<T>(ctx, aa);           // the whole analysis stage, by itself (persistent grid)
+        else if constexpr (sizeof(T) == 4) rc = launch_mdct(ctx, aa);               // fp32 mode: the stand-alone k_mdct
+        else if (ctx->LOGM == 10) rc = launch_mdct_only_t<double, 10>(ctx, aa);     // fp64 mode: sections A + C of k_analysis
+        else rc = launch_mdct_only_t<double, 9>(ctx, aa);
         if (rc) return rc;
         CK(cudaEventRecord(e1, ctx->stream));
         CK(cudaEventSynchronize(e1));

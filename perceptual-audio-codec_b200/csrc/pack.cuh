@@ -34,8 +34,7 @@ struct PackArgs {
     int perChunk;                     // 1: per-block API, payload only, at out + (w*2+ch)*cap
     int *overflow;                    // [S] set to 1 when a chunk would not fit
     const uint8_t *band_of_line;      // [M]
-    const uint32_t *codeLut;          // flattened code values   (PacHuffTables.code)
-    const uint8_t *lenLutFlat;        // flattened code lengths  (PacHuffTables.len)
+    const uint32_t *codeLen;          // flattened tables: code << 5 | length (0: the magnitude escapes), one load per line
     int32_t *o_mant;                  // optional [nchunk][M] signed mantissa codes at line positions (pre-zeroed)
     const uint8_t *header;            // prebuilt file header (pacfile.py:237-261), numSamples patched per stream
     int headerBytes;
@@ -114,8 +113,9 @@ k_pack(const PackArgs<T> a) {
                 sg = signbit((double)xv);                                  // np.signbit semantics (quantize.py:333): -0.0 counts
                 const unsigned mag = mant_mag(fabs((double)xv), sfb, largestScale, bab);
                 if (a.o_mant) a.o_mant[c * M + i] = (int32_t)(mag + (sg ? (1u << (bab - 1)) : 0u));
-                const int l = (int)mag < nkeys_t ? a.lenLutFlat[off_t + mag] : 0;
-                if (l) { code = a.codeLut[off_t + mag]; len = l; }
+                const unsigned cl = (int)mag < nkeys_t ? __ldg(a.codeLen + off_t + mag) : 0u;
+                const int l = (int)(cl & 31u);
+                if (l) { code = cl >> 5; len = l; }
                 else { code = escc; len = escl; code2 = mag; len2 = bab; }      // Huffman.py:296-298
             }
             int tl = len + len2;
