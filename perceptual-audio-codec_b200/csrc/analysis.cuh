@@ -480,12 +480,14 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     auto LI = [&](int j) { return FAST ? lineBase[j >> 1] + (j & 1) : tid + NT * j; };
     T zl[4], zlo[4], tiq[4], mld[4];
     int bnd[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int i = LI(j);
-        const double zd = a.tabd.zline[i];
-        zl[j] = (T)zd; zlo[j] = (T)(zd - (double)zl[j]);
-        tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
+    if constexpr (!FAST) {          // (fp32: section F fetches its two per-line constants when it needs them -- eight registers less to
+#pragma unroll                      //  carry through the six curves of a 64-register kernel)
+        for (int j = 0; j < 4; j++) {
+            int i = LI(j);
+            const double zd = a.tabd.zline[i];
+            zl[j] = (T)zd; zlo[j] = (T)(zd - (double)zl[j]);
+            tiq[j] = tb.tiq[i]; mld[j] = tb.mld[i]; bnd[j] = tb.band_of_line[i];
+        }
     }
 
     // fp32: bins whose upper skirt starts at or before the first / last line of this warp's two half-chunks (static)
@@ -718,6 +720,10 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         const uint32_t lrms = sm.lrms;
         T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
         T outl[2][4];
+        if constexpr (FAST) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { mld[j] = tb.mld[LI(j)]; bnd[j] = tb.band_of_line[LI(j)]; }
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int i = LI(j);

@@ -277,8 +277,11 @@ template <typename T, int LOGM>
 struct SynthSmem {
     static constexpr int M = 1 << LOGM;
     using T2 = typename Vec2<T>::type;
-    T2 W[2][M / 2 + 2];          // folded spectrum / FFT workspace
-    T v[2][M];                   // DCT-IV output
+    // fp32, 1024 lines: the register-blocked radix-8 passes want one spare element per 8 in W (fft.cuh: pad8) and one spare float per 16
+    // in v (the last pass writes frequencies 8 apart per lane); the radix-4 path of the other instantiations ignores the padding
+    static constexpr int WROW = M / 2 + M / 16 + 2;
+    T2 W[2][WROW];               // folded spectrum / FFT workspace
+    T v[2][M + M / 16];          // DCT-IV output
     uint16_t meta[2][kMaxBands];
     float gain[2][kMaxBands];    // fp32 mode: 2/(2^R-1) * 2^(largestScale-sf-1-overallScale) per band
     // double-buffered cp.async landing area: block b+1's codes and band metadata arrive while block b is transformed
@@ -326,11 +329,13 @@ __device__ __forceinline__ T synth_line(const SynthArgs<T> &a, const SS &sm, int
 }
 
 template <typename T, int LOGM>
-__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? 6 : 1)
+__global__ void __launch_bounds__((1 << LOGM) / 4, sizeof(T) == 4 ? 5 : 1)
 k_synth(const SynthArgs<T> a) {
     using SS = SynthSmem<T, LOGM>;
     using T2 = typename Vec2<T>::type;
     constexpr int M = SS::M, N = 2 * M, NT = M / 4, H = M / 2;
+    constexpr bool R8 = sizeof(T) == 4 && LOGM == 10;        // fp32, 1024 lines: register-blocked radix-8 FFT (see below)
+    auto VI = [](int i) { return R8 ? i + (i >> 4) : i; };   // position of v[i]
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SS &sm = *reinterpret_cast<SS *>(smem_raw);
     const int tid = threadIdx.x;
@@ -403,16 +408,69 @@ k_synth(const SynthArgs<T> a) {
             if ((lrms >> bA) & 1u) { a0 = a0 - a1; a1 = a0 + a1; }
             if ((lrms >> bB) & 1u) { b0 = b0 - b1; b1 = b0 + b1; }
             const T2 pre = tb.mdct_pre[n];
-            sm.W[0][n] = cmul(mk2<T>(a0, b0), pre);
-            sm.W[1][n] = cmul(mk2<T>(a1, b1), pre);
+            sm.W[0][R8 ? pad8(n) : n] = cmul(mk2<T>(a0, b0), pre);
+            sm.W[1][R8 ? pad8(n) : n] = cmul(mk2<T>(a1, b1), pre);
         }
         __syncthreads();
-        fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, H + 2, tb.tw, 2);
-        for (int e = tid; e < 2 * H; e += NT) {
-            int ch = e / H, k = e - ch * H;
-            T2 yv = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
-            sm.v[ch][2 * k] = yv.x;                 // v[2k]
-            sm.v[ch][M - 1 - 2 * k] = -yv.y;        // v[M-1-2k]
+        if constexpr (R8) {
+            // H = 512 complex points per channel as radix 8 x 8 x 8, one 8-point DFT per thread and pass held in registers (threads
+            // 0..63 channel 0, 64..127 channel 1; the other half of the CTA idles through the three short passes): 3 passes through
+            // shared memory instead of 5, and the last one applies the DCT-IV post-twiddle and writes v directly.
+            if (tid < 2 * (H / 8)) {
+                const int ch = tid / (H / 8), t = tid - ch * (H / 8);
+                T2 *Z = sm.W[ch];
+                T2 x[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) x[r] = Z[pad8(t + (H / 8) * r)];
+                dft8(x);
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    T2 y = x[brev3(p)];
+                    if (p) y = cmul(y, tb.tw[2 * t * p]);                 // W_H^(t p), tw[m] = exp(-2 pi i m / M)
+                    Z[pad8(t + (H / 8) * p)] = y;
+                }
+            }
+            __syncthreads();
+            if (tid < 2 * (H / 8)) {
+                const int ch = tid / (H / 8), t = tid - ch * (H / 8);
+                const int g = t >> 3, j = t & 7;
+                T2 *Z = sm.W[ch];
+                T2 x[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) x[r] = Z[pad8(64 * g + j + 8 * r)];
+                dft8(x);
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    T2 y = x[brev3(p)];
+                    if (p) y = cmul(y, tb.tw[16 * j * p]);                // W_64^(j p)
+                    Z[pad8(64 * g + j + 8 * p)] = y;
+                }
+            }
+            __syncthreads();
+            if (tid < 2 * (H / 8)) {
+                const int ch = tid / (H / 8), t = tid - ch * (H / 8);
+                const T2 *Z = sm.W[ch];
+                T2 x[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) x[r] = Z[pad8(8 * t + r)];
+                dft8(x);
+                const int kb = (t >> 3) + 8 * (t & 7);                    // frequency k = kb + 64 p
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    const int k = kb + 64 * p;
+                    const T2 yv = cmul(x[brev3(p)], tb.mdct_post[k]);
+                    sm.v[ch][VI(2 * k)] = yv.x;                           // v[2k]
+                    sm.v[ch][VI(M - 1 - 2 * k)] = -yv.y;                  // v[M-1-2k]
+                }
+            }
+        } else {
+            fft_dif<T, LOGM - 1, NT>(&sm.W[0][0], 2, SS::WROW, tb.tw, 2);
+            for (int e = tid; e < 2 * H; e += NT) {
+                int ch = e / H, k = e - ch * H;
+                T2 yv = cmul(sm.W[ch][fft_pos<LOGM - 1>(k)], tb.mdct_post[k]);
+                sm.v[ch][2 * k] = yv.x;                 // v[2k]
+                sm.v[ch][M - 1 - 2 * k] = -yv.y;        // v[M-1-2k]
+            }
         }
         __syncthreads();
         // unfold (IMDCT, mdct.py:73-80: y[n] = 2 sum_k X[k] cos(2pi/N (n+n0)(k+1/2))), SineWindow (codec.py:59-60),
@@ -427,7 +485,7 @@ k_synth(const SynthArgs<T> a) {
             short2 o;
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
-                T vF = sm.v[ch][iF], vS = -sm.v[ch][iS];
+                T vF = sm.v[ch][VI(iF)], vS = -sm.v[ch][VI(iS)];
                 if (i >= H) vF = -vF;
                 const T yF = (T)2 * vF * wF, yS = (T)2 * vS * wS;
                 if (a.rawOut) {

@@ -195,6 +195,34 @@ __device__ __forceinline__ void fft1024_r16(float2 *buf, int nbatch, int bstride
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Radix-8 building blocks of the register-blocked M/2-point FFTs (encoder k_mdct_enc in fp64, decoder k_synth in fp32).
+// pad8: one spare element per 8 -- the radix-8 passes, the autosorting write and the natural-order reads are conflict-free.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
+
+template <typename V> __device__ __forceinline__ void radix2(V &a, V &b) { const V t = csub(a, b); a = cadd(a, b); b = t; }
+
+// in-register 8-point DFT (decimation in frequency), output y[p] left in x[brev3(p)]
+template <typename V>
+__device__ __forceinline__ void dft8(V (&x)[8]) {
+    using T = decltype(x[0].x);
+    const T H = (T)0.70710678118654752440;
+#pragma unroll
+    for (int i = 0; i < 4; i++) radix2(x[i], x[i + 4]);
+    // twiddles W8^i on the lower half: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2
+    { const V t = x[5]; x[5].x = (t.x + t.y) * H; x[5].y = (t.y - t.x) * H; }
+    { const V t = x[6]; x[6].x = t.y; x[6].y = -t.x; }
+    { const V t = x[7]; x[7].x = (t.y - t.x) * H; x[7].y = -(t.x + t.y) * H; }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        radix2(x[h], x[h + 2]); radix2(x[h + 1], x[h + 3]);
+        { const V t = x[h + 3]; x[h + 3].x = t.y; x[h + 3].y = -t.x; }       // W4^1 = -i
+        radix2(x[h], x[h + 1]); radix2(x[h + 2], x[h + 3]);
+    }
+}
+__device__ __forceinline__ int brev3(int p) { return ((p & 1) << 2) | (p & 2) | (p >> 2); }
+
 // X[k] (0 <= k <= M) of a real sequence whose packed (even + i*odd) M-point FFT sits in Z (digit-reversed).
 template <typename T, int LOGM, bool PAD = false, bool R16 = false>
 __device__ __forceinline__ typename Vec2<T>::type rfft_split(const typename Vec2<T>::type *Z, int k,

@@ -11,6 +11,7 @@
 // Algebra as tests/model_analysis.py:mdct_fold_fft (DCT-IV by an M/2-point complex FFT).
 #pragma once
 #include "common.cuh"
+#include "fft.cuh"
 
 namespace pac {
 
@@ -28,36 +29,14 @@ struct MdctArgs {
     DevTables<double> tabd;
 };
 
-// one spare element per 8: the radix-8 passes, the autosorting write and the natural-order read are all conflict-free for
-// 16-byte elements (a quarter warp covers the eight 16-byte bank groups)
-__device__ __forceinline__ int mdct_pad(int i) { return i + (i >> 3); }
-
-__device__ __forceinline__ void radix2_d(double2 &a, double2 &b) { const double2 t = csub(a, b); a = cadd(a, b); b = t; }
-
-// in-register 8-point DFT (decimation in frequency), output y[p] left in x[bitrev3(p)]
-__device__ __forceinline__ void dft8_d(double2 (&x)[8]) {
-    const double H = 0.70710678118654752440;
-#pragma unroll
-    for (int i = 0; i < 4; i++) radix2_d(x[i], x[i + 4]);
-    // twiddles W8^i on the lower half: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2
-    x[5] = mk2<double>((x[5].x + x[5].y) * H, (x[5].y - x[5].x) * H);
-    x[6] = mk2<double>(x[6].y, -x[6].x);
-    x[7] = mk2<double>((x[7].y - x[7].x) * H, -(x[7].x + x[7].y) * H);
-#pragma unroll
-    for (int h = 0; h < 8; h += 4) {
-        radix2_d(x[h], x[h + 2]); radix2_d(x[h + 1], x[h + 3]);
-        x[h + 3] = mk2<double>(x[h + 3].y, -x[h + 3].x);       // W4^1 = -i
-        radix2_d(x[h], x[h + 1]); radix2_d(x[h + 2], x[h + 3]);
-    }
-}
-__device__ __forceinline__ int brev3(int p) { return ((p & 1) << 2) | (p & 2) | (p >> 2); }
-
 template <int LOGM>
 struct EncMdctSmem {
     static constexpr int M = 1 << LOGM, H = M / 2;
     double2 Z[2][H + H / 8];     // folded points / FFT work per channel (padded)
-    float v[2][M];               // unscaled lines, staged for the coalesced store
-    int pcm[2 * M];              // the block's 2048 stereo frames (int16 pairs)
+    union {                      // the window's samples are dead once folded; the same 8 KB then stage the lines
+        int pcm[2 * M];          // the block's 2048 stereo frames (int16 pairs)
+        float v[2][M];           // unscaled lines, staged for the coalesced store
+    };
     double red[2][4];
     int oscale[2];
 };
@@ -121,7 +100,7 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
             for (int c = 0; c < 2; c++) {
                 const double u0 = m0 < H ? -xw(c, 3 * H - 1 - m0) - xw(c, 3 * H + m0) : xw(c, m0 - H) - xw(c, 2 * H - 1 - (m0 - H));
                 const double u1 = m1 < H ? -xw(c, 3 * H - 1 - m1) - xw(c, 3 * H + m1) : xw(c, m1 - H) - xw(c, 2 * H - 1 - (m1 - H));
-                sm.Z[c][mdct_pad(n)] = cmul(mk2<double>(u0, u1), pre);
+                sm.Z[c][pad8(n)] = cmul(mk2<double>(u0, u1), pre);
             }
         }
         __syncthreads();
@@ -132,13 +111,13 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
             const int j = t;                                 // HT == L
             double2 x[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) x[r] = Z[mdct_pad(j + L * r)];
-            dft8_d(x);
+            for (int r = 0; r < 8; r++) x[r] = Z[pad8(j + L * r)];
+            dft8(x);
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 double2 y = x[brev3(p)];
                 if (p) y = cmul(y, td.tw[2 * j * p]);
-                Z[mdct_pad(j + L * p)] = y;
+                Z[pad8(j + L * p)] = y;
             }
         }
         __syncthreads();
@@ -147,13 +126,13 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
             const int g = t / L2, j = t - g * L2;
             double2 x[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) x[r] = Z[mdct_pad(L1 * g + j + L2 * r)];
-            dft8_d(x);
+            for (int r = 0; r < 8; r++) x[r] = Z[pad8(L1 * g + j + L2 * r)];
+            dft8(x);
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 double2 y = x[brev3(p)];
                 if (p) y = cmul(y, td.tw[2 * 8 * j * p]);
-                Z[mdct_pad(L1 * g + j + L2 * p)] = y;
+                Z[pad8(L1 * g + j + L2 * p)] = y;
             }
         }
         __syncthreads();
@@ -168,15 +147,15 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
             for (int u = 0; u < PER; u++) {
                 const int g = t + HT * u;                    // sub-transform index: p1 = g / 8, p2 = g % 8
 #pragma unroll
-                for (int r = 0; r < R3; r++) x[r] = Z[mdct_pad(R3 * g + r)];
+                for (int r = 0; r < R3; r++) x[r] = Z[pad8(R3 * g + r)];
                 if (R3 == 8) {
-                    dft8_d(x);
+                    dft8(x);
 #pragma unroll
                     for (int p = 0; p < 8; p++) y[u][p] = x[brev3(p)];
                 } else {
-                    radix2_d(x[0], x[2]); radix2_d(x[1], x[3]);
+                    radix2(x[0], x[2]); radix2(x[1], x[3]);
                     x[3] = mk2<double>(x[3].y, -x[3].x);
-                    radix2_d(x[0], x[1]); radix2_d(x[2], x[3]);
+                    radix2(x[0], x[1]); radix2(x[2], x[3]);
                     y[u][0] = x[0]; y[u][1] = x[2]; y[u][2] = x[1]; y[u][3] = x[3];
                 }
             }
@@ -186,14 +165,14 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
                 const int g = t + HT * u;
                 const int kb = (g >> 3) + 8 * (g & 7);
 #pragma unroll
-                for (int p = 0; p < R3; p++) Z[mdct_pad(kb + 64 * p)] = y[u][p];
+                for (int p = 0; p < R3; p++) Z[pad8(kb + 64 * p)] = y[u][p];
             }
         }
         __syncthreads();
         // ---- post-twiddle: X[2k] = (2/N) Re(y_k e^{-i pi (k + 1/4)/M}), X[M-1-2k] = -(2/N) Im(...); block maximum per channel
         double mx = 0.0;
         for (int k = t; k < H; k += HT) {
-            const double2 y = cmul(Z[mdct_pad(k)], td.mdct_post[k]);
+            const double2 y = cmul(Z[pad8(k)], td.mdct_post[k]);
             const double v0 = (2.0 / (double)N) * y.x, v1 = -(2.0 / (double)N) * y.y;
             sm.v[ch][2 * k] = (float)v0;                     // rounding to fp32 commutes with the power-of-two overall scale
             sm.v[ch][M - 1 - 2 * k] = (float)v1;
