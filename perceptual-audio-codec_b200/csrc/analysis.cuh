@@ -361,7 +361,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
     //    its value extrapolated to the half-chunk's first line.  Maskers whose bound lies 30 bits below the smallest partial
     //    threshold of the half-chunk (lower skirts + plateaus + quiet skirts + threshold in quiet are already in) cannot change
     //    a float sum: each lane tests one masker, a ballot keeps the survivors (about a third on the synthetic corpus), and the
-    //    pairwise loop walks only those.  <= 512 maskers x 2^-30: 5e-7 relative, 2e-6 dB.
+    //    pairwise loop walks only those.  <= 512 maskers x 2^-26: 8e-6 relative, 3e-5 dB (the 1e-5 budget on SMR is 1e-4 dB).
     float acc[4];
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
@@ -388,7 +388,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
         if (mhi > 0) {
             // positive floats order like their bit patterns: one REDUX gives the smallest partial threshold of the half-chunk
             const float lmin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(x0, x1))));
-            const float cut = lg2_approx(lmin) - 30.01f;
+            const float cut = lg2_approx(lmin) - 26.01f;
             const float zc = __shfl_sync(0xffffffffu, z0, 0);             // Bark position of the half-chunk's first line
             for (int base = 0; base < mhi; base += 32) {
                 const int mm = base + lane;

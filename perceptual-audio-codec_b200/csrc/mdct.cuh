@@ -37,12 +37,14 @@ struct EncMdctSmem {
         int pcm[2 * M];          // the block's 2048 stereo frames (int16 pairs)
         float v[2][M];           // unscaled lines, staged for the coalesced store
     };
+    double2 twH[H];              // exp(-2 pi i m / H): the first pass's twiddles (fetched per CTA once; as global loads they missed the
+    double2 twL[H / 8];          // small L1 this kernel leaves and sat on the L2 latency, ncu); exp(-2 pi i m / (H/8)) for the second pass
     double red[2][4];
     int oscale[2];
 };
 
 // CTA = M/8 threads: the first half works on channel 0 in the FFT passes, the second on channel 1
-template <int LOGM>
+template <int LOGM, bool PCM>
 __global__ void __launch_bounds__((1 << LOGM) / 8)
 k_mdct_enc(const __grid_constant__ MdctArgs a) {
     using SM = EncMdctSmem<LOGM>;
@@ -55,35 +57,54 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevTables<double> &td = a.tabd;
     const int ch = tid / HT, t = tid - ch * HT;              // FFT role
-    for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    for (int m = tid; m < H; m += NT) sm.twH[m] = td.tw[2 * m];
+    for (int m = tid; m < H / 8; m += NT) sm.twL[m] = td.tw[16 * m];
+    // the window [(b-1) M, (b+1) M) of work item w, zero outside [0, n): 16-byte loads (4 stereo frames) into registers.  The NEXT
+    // item's window is requested before the current one is transformed, so its HBM latency hides behind the transform.
+    constexpr int NV = N / 4 / NT;                          // int4 per thread
+    int4 win[NV];
+    auto fetch = [&](int64_t w) -> bool {
         const int s = a.nwork <= 0xffffffffll ? (int)((uint32_t)w / (uint32_t)a.nb) : (int)(w / a.nb);
         const int b = a.b0 + (int)(w - (int64_t)s * a.nb);
-        // ---- load the 2048-frame window [(b-1) M, (b+1) M), zero outside [0, n): 16-byte loads (4 stereo frames)
-        if (a.pcm) {
-            const int64_t ns = a.nSamples[s];
-            const int64_t nblk = (ns + M - 1) / M + 1;
-            if (b >= nblk) continue;                         // uniform for the CTA
-            const int *p32 = reinterpret_cast<const int *>(a.pcm) + (int64_t)s * a.strideSamples;
-            const int64_t base = (int64_t)(b - 1) * M;
-            const bool vec = ((reinterpret_cast<uintptr_t>(p32) & 15) == 0) && ((a.strideSamples & 3) == 0);   // row base 16-byte aligned
-            for (int q = tid; q < N / 4; q += NT) {
-                const int64_t si = base + 4 * q;             // base is a multiple of M, so 4-frame groups are aligned
-                int4 v4 = make_int4(0, 0, 0, 0);
-                if (si >= 0 && si + 4 <= ns && vec) v4 = __ldg(reinterpret_cast<const int4 *>(p32 + si));
-                else if (si + 4 > 0 && si < ns) {
-                    int r[4];
+        const int64_t ns = a.nSamples[s];
+        const int64_t nblk = (ns + M - 1) / M + 1;
+        if (b >= nblk) return false;                         // uniform for the CTA
+        const int *p32 = reinterpret_cast<const int *>(a.pcm) + (int64_t)s * a.strideSamples;
+        const int64_t base = (int64_t)(b - 1) * M;
+        const bool vec = (reinterpret_cast<uintptr_t>(p32) & 15) == 0;        // row base 16-byte aligned
 #pragma unroll
-                    for (int j = 0; j < 4; j++) r[j] = (si + j >= 0 && si + j < ns) ? __ldg(p32 + si + j) : 0;
-                    v4 = make_int4(r[0], r[1], r[2], r[3]);
-                }
-                *reinterpret_cast<int4 *>(&sm.pcm[4 * q]) = v4;
+        for (int i = 0; i < NV; i++) {
+            const int64_t si = base + 4 * (tid + NT * i);    // base is a multiple of M, so 4-frame groups are aligned
+            int4 v4 = make_int4(0, 0, 0, 0);
+            if (si >= 0 && si + 4 <= ns && vec) v4 = __ldg(reinterpret_cast<const int4 *>(p32 + si));
+            else if (si + 4 > 0 && si < ns) {
+                int r[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) r[j] = (si + j >= 0 && si + j < ns) ? __ldg(p32 + si + j) : 0;
+                v4 = make_int4(r[0], r[1], r[2], r[3]);
             }
+            win[i] = v4;
+        }
+        return true;
+    };
+    bool have = false;
+    if (PCM && (int64_t)blockIdx.x < a.nwork) have = fetch(blockIdx.x);
+    __syncthreads();
+    for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+        if (PCM) {
+            const bool cur = have;
+            if (cur) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) *reinterpret_cast<int4 *>(&sm.pcm[4 * (tid + NT * i)]) = win[i];
+            }
+            have = (w + gridDim.x < a.nwork) ? fetch(w + gridDim.x) : false;
+            if (!cur) continue;                              // a block past the end of its stream (uniform for the CTA)
             __syncthreads();
         }
         // windowed sample n of channel c as the reference forms it: x = +-2|code|/65535 (quantize.py:141; -32768 -> 0), times sin
         auto xw = [&](int c, int n) -> double {
             double v;
-            if (a.pcm) {
+            if (PCM) {
                 const int pr = sm.pcm[n];
                 const int sv = c ? (pr >> 16) : (int)(short)(pr & 0xffff);
                 int code = sv < 0 ? -sv : sv;
@@ -116,7 +137,7 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 double2 y = x[brev3(p)];
-                if (p) y = cmul(y, td.tw[2 * j * p]);
+                if (p) y = cmul(y, sm.twH[j * p]);
                 Z[pad8(j + L * p)] = y;
             }
         }
@@ -131,7 +152,7 @@ k_mdct_enc(const __grid_constant__ MdctArgs a) {
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 double2 y = x[brev3(p)];
-                if (p) y = cmul(y, td.tw[2 * 8 * j * p]);
+                if (p) y = cmul(y, sm.twL[j * p]);
                 Z[pad8(L1 * g + j + L2 * p)] = y;
             }
         }

@@ -702,14 +702,17 @@ static int launch_mdct_only_t(PacCtx *ctx, AnalysisArgs<T> &a) {
 }
 
 // K1 of the fp32 fast mode: window + MDCT + overall scale as their own fp64 kernel (mdct.cuh), one CTA per stereo block
-template <int LOGM>
+template <int LOGM, bool PCM>
 static int launch_mdct_t(PacCtx *ctx, const MdctArgs &m) {
     const size_t smem = sizeof(EncMdctSmem<LOGM>);
-    CK(cudaFuncSetAttribute(k_mdct_enc<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (int64_t)ctx->numSMs * 32;
+    CK(cudaFuncSetAttribute(k_mdct_enc<LOGM, PCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSM = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_mdct_enc<LOGM, PCM>, (1 << LOGM) / 8, smem));
+    if (perSM < 1) perSM = 1;
+    int64_t grid = (int64_t)ctx->numSMs * perSM * 2;          // a few work items per CTA: the twiddle tables are staged once per CTA
     if (grid > m.nwork) grid = m.nwork;
     if (grid < 1) grid = 1;
-    { KTimer kt(ctx, PAC_K_MDCT); k_mdct_enc<LOGM><<<(unsigned)grid, (1 << LOGM) / 8, smem, LS(ctx)>>>(m); }
+    { KTimer kt(ctx, PAC_K_MDCT); k_mdct_enc<LOGM, PCM><<<(unsigned)grid, (1 << LOGM) / 8, smem, LS(ctx)>>>(m); }
     ctx->launches++;
     CK(cudaGetLastError());
     return PAC_OK;
@@ -722,8 +725,8 @@ static int launch_mdct(PacCtx *ctx, const AnalysisArgs<float> &a) {
     m.lines = a.lines; m.oscale = a.oscale;
     int rc = get_tables<double>(ctx, ctx->N, &m.tabd);
     if (rc) return rc;
-    if (ctx->LOGM == 10) return launch_mdct_t<10>(ctx, m);
-    if (ctx->LOGM == 9) return launch_mdct_t<9>(ctx, m);
+    if (ctx->LOGM == 10) return m.pcm ? launch_mdct_t<10, true>(ctx, m) : launch_mdct_t<10, false>(ctx, m);
+    if (ctx->LOGM == 9) return m.pcm ? launch_mdct_t<9, true>(ctx, m) : launch_mdct_t<9, false>(ctx, m);
     FAIL(PAC_E_ARG, "unsupported nMDCTLines");
 }
 static int launch_mdct(PacCtx *, const AnalysisArgs<double> &) { return PAC_OK; }     // fp64 mode: the MDCT is a section of k_analysis

@@ -103,9 +103,9 @@ k_pack(const PackArgs<T> a) {
         for (int g = 0; g < nGroups; g++) {
             const int i0 = 32 * g, i = i0 + lane;
             const int bd = a.band_of_line[i];
+            const T xv = x[i];
             const unsigned pb = __shfl_sync(0xffffffffu, pbL, bd);
             const int bab = (int)(pb & 0xff), sfb = (int)(pb >> 8);
-            const T xv = x[i];
             unsigned code = 0, code2 = 0;
             int len = 0, len2 = 0;
             bool sg = false;

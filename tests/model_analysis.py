@@ -277,7 +277,7 @@ def curve_v3(T, G, F, drop, dtype=np.float32, stats=None):
             lo, hi = 64 * h, 64 * h + 64
             if i0 >= hi:
                 continue
-            cut = np.log2(np.float64(part[lo:hi].min())) - 30.01
+            cut = np.log2(np.float64(part[lo:hi].min())) - 26.01
             if dtype(np.float64(up) * dtype(zl[lo]) + dtype(B)) < cut:
                 nculled += hi - max(lo, i0)
                 continue
