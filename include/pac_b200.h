@@ -47,7 +47,14 @@ typedef struct {
     int32_t nMantSizeBits;        /* 4 */
     int32_t nTableIDBits;         /* 4 */
     double  targetBitsPerSample;  /* 2.27 */
+    int32_t window;               /* PAC_WINDOW_SINE (what HEAD's codec calls, codec.py:59-60,239-240) or PAC_WINDOW_KBD: the same two
+                                   * call sites with window.KBDWindow (window.py:56-78, alpha = 4) in place of SineWindow.  KBDWindow
+                                   * returns a COPY, so -- unlike the in-place SineWindow -- the psychoacoustic model
+                                   * then sees the un-windowed block. */
+    int32_t reserved;
 } PacParams;
+#define PAC_WINDOW_SINE 0
+#define PAC_WINDOW_KBD  1
 
 /* huffmanTables.pickle flattened by the host shim (Huffman.py:138-153, 256-262): for table ID t+1,
  * magnitude v < nkeys[t] has code value code[off[t]+v] of len[off[t]+v] bits; len 0 = key absent

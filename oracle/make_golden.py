@@ -115,6 +115,42 @@ def make_files(jobs):
           % (len(recs), sum(1 for r in recs if r.get("committed_golden"))))
 
 
+def make_kbd():
+    """KBDWindow as the codec's window: the REFERENCE's own encode and decode with the name `SineWindow` in codec.py's
+    namespace rebound to window.KBDWindow (codec.py:59-60 and :239-240 are its only two uses on the path) -- no source edited, the
+    reference's KBDWindow (window.py:56-78: alpha = 4, returns a copy) does the windowing.  Pins the oracle's and the engine's
+    PAC_WINDOW_KBD option on a 40-block clip of piano_test2 (tests/golden/kbd_piano.*)."""
+    tmp = tempfile.mkdtemp(prefix="pac_gold_kbd_")
+    try:
+        with ref_py3.Ref() as R:
+            import struct
+            src = open(os.path.join(REF_INPUTS, "piano_test2.wav"), "rb").read()
+            p = src.find(b"data")
+            n = 40 * 1024 + 100
+            body = src[p + 8:p + 8 + n * 4]
+            hdr = bytearray(src[:p + 8])
+            hdr[p + 4:p + 8] = struct.pack("<L", len(body))
+            hdr[4:8] = struct.pack("<L", len(hdr) - 8 + len(body))
+            wav = os.path.join(tmp, "kbd_piano.wav")
+            open(wav, "wb").write(bytes(hdr) + body)
+            assert R.codec.SineWindow is R.window.SineWindow
+            R.codec.SineWindow = R.window.KBDWindow
+            pac = os.path.join(tmp, "kbd_piano.wak")
+            out = os.path.join(tmp, "kbd_piano.out.wav")
+            sys.stdout = open(os.devnull, "w")
+            dep, extra = R.encode_file(wav, pac)
+            R.decode_file(pac, out)
+            sys.stdout = sys.__stdout__
+            for f in ("kbd_piano.wav", "kbd_piano.wak", "kbd_piano.out.wav"):
+                shutil.copyfile(os.path.join(tmp, f), os.path.join(GOLD, f))
+            with open(os.path.join(GOLD, "kbd_piano.json"), "w") as f:
+                json.dump({"bitDeposit_end": int(dep), "extraBits_end": int(extra), "pac_bytes": os.path.getsize(pac),
+                           "generator": "oracle/make_golden.py --only kbd: patched reference with codec.SineWindow = window.KBDWindow"}, f)
+            print("kbd: %d bytes coded, final state (%d, %d)" % (os.path.getsize(pac), dep, extra))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def make_stages():
     """Per-stage taps, captured by wrapping the reference's own functions."""
     want = {}
@@ -443,6 +479,8 @@ def main():
         make_kats()
     if a.only in ("", "stages"):
         make_stages()
+    if a.only in ("", "kbd"):
+        make_kbd()
     if a.only in ("", "files"):
         make_files(a.jobs)
 

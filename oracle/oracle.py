@@ -38,7 +38,7 @@ def build(force=False):
 class OrcParams(C.Structure):
     _fields_ = [("sampleRate", C.c_int32), ("nChannels", C.c_int32), ("nMDCTLines", C.c_int32),
                 ("nScaleBits", C.c_int32), ("nMantSizeBits", C.c_int32), ("nTableIDBits", C.c_int32),
-                ("targetBitsPerSample", C.c_double)]
+                ("targetBitsPerSample", C.c_double), ("window", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OrcHuff(C.Structure):
@@ -98,8 +98,8 @@ def flatten_tables(tables):
             np.concatenate(lens), np.array(esc_code, np.uint32), np.array(esc_len, np.int32))
 
 
-def default_params(sampleRate=44100, target=2.27):
-    return OrcParams(sampleRate, 2, 1024, 4, 4, 4, target)
+def default_params(sampleRate=44100, target=2.27, window=0):
+    return OrcParams(sampleRate, 2, 1024, 4, 4, 4, target, window, 0)
 
 
 def read_wav(path):
@@ -187,6 +187,9 @@ class Oracle:
         L.orc_decode_stream.argtypes = [C.POINTER(OrcHuff), C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int16),
                                         C.c_int64, C.POINTER(OrcParams), C.POINTER(C.c_int64)]
         L.orc_decode_stream.restype = C.c_int64
+        L.orc_decode_stream_w.argtypes = [C.POINTER(OrcHuff), C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int16),
+                                          C.c_int64, C.POINTER(OrcParams), C.POINTER(C.c_int64), C.c_int]
+        L.orc_decode_stream_w.restype = C.c_int64
         L.orc_encode_batch.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcHuff), C.POINTER(C.c_int16), C.c_int64, C.c_int,
                                        C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int64), C.c_int]
 
@@ -308,7 +311,7 @@ class Oracle:
             raise RuntimeError("orc_encode_stream failed: %d" % r)
         return out[:r].tobytes(), tr, (int(fs[0]), int(fs[1]))
 
-    def decode_stream(self, pac):
+    def decode_stream(self, pac, window=0):
         """pac bytes -> (pcm int16 [n][2], sampleRate, numSamples from the header)"""
         buf = np.frombuffer(pac, dtype=np.uint8).copy()
         nblocks_upper = len(buf) // 8 + 2
@@ -316,8 +319,8 @@ class Oracle:
         pcm = np.zeros((cap, 2), dtype=np.int16)
         hdr = OrcParams()
         ns = C.c_int64()
-        r = self.lib.orc_decode_stream(C.byref(self.huff), _ptr(buf, C.c_uint8), len(buf), _ptr(pcm, C.c_int16), cap,
-                                       C.byref(hdr), C.byref(ns))
+        r = self.lib.orc_decode_stream_w(C.byref(self.huff), _ptr(buf, C.c_uint8), len(buf), _ptr(pcm, C.c_int16), cap,
+                                         C.byref(hdr), C.byref(ns), int(window))
         if r < 0:
             raise RuntimeError("orc_decode_stream failed: %d" % r)
         return pcm[:r].copy(), int(hdr.sampleRate), int(ns.value)

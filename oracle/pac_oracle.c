@@ -714,8 +714,15 @@ int64_t orc_encode_stream(const OrcParams *p, const OrcHuff *h, const int16_t *p
         }
         int32_t overallScale[2];
         for (int ch = 0; ch < 2; ch++) {                        /* :237-246 */
-            orc_sine_window(full + ch * N, N);
-            orc_mdct(full + ch * N, halfN, halfN, mdct + ch * halfN);
+            if (p->window == 1) {                               /* KBDWindow returns a copy (window.py:64): `full` stays un-windowed */
+                double *tmpw = (double *)malloc((size_t)N * sizeof(double));
+                orc_kbd_window(full + ch * N, tmpw, N, 4.0);
+                orc_mdct(tmpw, halfN, halfN, mdct + ch * halfN);
+                free(tmpw);
+            } else {
+                orc_sine_window(full + ch * N, N);              /* in place: the psychoacoustic model sees it (window.py:37) */
+                orc_mdct(full + ch * N, halfN, halfN, mdct + ch * halfN);
+            }
             double maxLine = 0.0;
             for (int i = 0; i < halfN; i++) if (fabs(mdct[ch * halfN + i]) > maxLine) maxLine = fabs(mdct[ch * halfN + i]);
             overallScale[ch] = orc_scale_factor(maxLine, p->nScaleBits, 5);
@@ -859,6 +866,12 @@ static void trie_build(Trie *t, const OrcHuff *h, int tab)
 int64_t orc_decode_stream(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, int16_t *pcm, int64_t capSamples,
                           OrcParams *hdr_out, int64_t *numSamplesHdr)
 {
+    return orc_decode_stream_w(h, pac, nbytes, pcm, capSamples, hdr_out, numSamplesHdr, 0);
+}
+
+int64_t orc_decode_stream_w(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, int16_t *pcm, int64_t capSamples,
+                            OrcParams *hdr_out, int64_t *numSamplesHdr, int window)
+{
     /* ---- header, pacfile.py:123-151 ---- */
     if (nbytes < 26 || memcmp(pac, "PAC ", 4)) return -1;
     OrcParams p;
@@ -869,6 +882,7 @@ int64_t orc_decode_stream(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, 
     p.nScaleBits = (int32_t)get_le16(pac + 18);
     p.nMantSizeBits = (int32_t)get_le16(pac + 20);
     p.nTableIDBits = 4;                                          /* pacfile.py:189 */
+    p.window = window; p.reserved = 0;
     p.targetBitsPerSample = 0;
     int nBands = (int)get_le32(pac + 22);
     if (p.nChannels != 2 || nBands > ORC_MAX_BANDS || nbytes < 26 + 2 * nBands) return -1;
@@ -945,7 +959,12 @@ int64_t orc_decode_stream(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, 
         }
         for (int ch = 0; ch < 2; ch++) {                         /* :59-60 */
             orc_imdct(line + ch * halfN, halfN, halfN, dec + ch * N);
-            orc_sine_window(dec + ch * N, N);
+            if (window == 1) {
+                double *tmpw = (double *)malloc((size_t)N * sizeof(double));
+                orc_kbd_window(dec + ch * N, tmpw, N, 4.0);
+                memcpy(dec + ch * N, tmpw, (size_t)N * sizeof(double));
+                free(tmpw);
+            } else orc_sine_window(dec + ch * N, N);
         }
         /* overlap-add, pacfile.py:223-226; __main__ drops the first block, pacfile.py:485-487 */
         if (!first) {

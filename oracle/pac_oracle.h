@@ -29,6 +29,10 @@ typedef struct {
     int32_t nMantSizeBits;        /* pacfile.py:454 */
     int32_t nTableIDBits;         /* pacfile.py:457 */
     double  targetBitsPerSample;  /* pacfile.py:455 */
+    int32_t window;               /* 0: SineWindow (codec.py:59-60,239-240 as HEAD has them); 1: the same two call sites with
+                                   * window.KBDWindow (window.py:56-78) -- which returns a COPY, so the psychoacoustic model then
+                                   * sees the un-windowed block (no Q1 aliasing) */
+    int32_t reserved;
 } OrcParams;
 
 /* Flattened huffmanTables.pickle (Huffman.py:138-153): for table t (ID t+1), magnitudes
@@ -110,6 +114,8 @@ int64_t orc_encoded_blocks(int64_t nSamples, int nMDCTLines);
 /* pac -> interleaved int16 PCM as the reference __main__ Decode pass writes it (first block dropped,
  * overlap tail emitted).  Returns samples per channel written, or <0 on error.
  * pacfile.py:123-229, codec.py:25-65, pcmfile.py:118-147 */
+int64_t orc_decode_stream_w(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, int16_t *pcm, int64_t capSamples,
+                            OrcParams *hdr_out, int64_t *numSamplesHdr, int window /* as OrcParams.window: the container does not store it */);
 int64_t orc_decode_stream(const OrcHuff *h, const uint8_t *pac, int64_t nbytes, int16_t *pcm, int64_t capSamples,
                           OrcParams *hdr_out, int64_t *numSamplesHdr);
 /* encode many equal-length streams on `nthreads` host threads (CPU baseline).  pcm [S][nSamples][2],

@@ -31,7 +31,7 @@ class PacError(Exception):
 class PacParams(C.Structure):
     _fields_ = [("sampleRate", C.c_int32), ("nChannels", C.c_int32), ("nMDCTLines", C.c_int32),
                 ("nScaleBits", C.c_int32), ("nMantSizeBits", C.c_int32), ("nTableIDBits", C.c_int32),
-                ("targetBitsPerSample", C.c_double)]
+                ("targetBitsPerSample", C.c_double), ("window", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PacHuffTables(C.Structure):
@@ -228,7 +228,7 @@ class Engine(object):
     """One context on one GPU (PacCtx).  precision: 'fp64' (verification, bit-exact) or 'fp32' (fast)."""
 
     def __init__(self, device=0, precision="fp64", sampleRate=44100, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4,
-                 nTableIDBits=4, targetBitsPerSample=2.27, tables=None):
+                 nTableIDBits=4, targetBitsPerSample=2.27, tables=None, window="sine"):
         L = lib()
         self.tables = tables if tables is not None else load_encoding_tables()
         (self._nkeys, self._off, self._code, self._len, self._esc_code, self._esc_len) = flatten_tables(self.tables)
@@ -239,7 +239,7 @@ class Engine(object):
         h.code = _p(self._code, C.c_uint32)
         h.len = _p(self._len, C.c_uint8)
         self.params = PacParams(int(sampleRate), 2, int(nMDCTLines), int(nScaleBits), int(nMantSizeBits), int(nTableIDBits),
-                                float(targetBitsPerSample))
+                                float(targetBitsPerSample), {"sine": 0, "kbd": 1}[window], 0)
         self.precision = {"fp64": PAC_PRECISION_FP64, "fp32": PAC_PRECISION_FP32}[precision]
         self.precision_name = precision
         self.device = device
@@ -576,12 +576,12 @@ def set_default(device=None, precision=None):
 
 
 def engine(sampleRate=44100, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4, nTableIDBits=4, targetBitsPerSample=2.27,
-           device=None, precision=None):
+           device=None, precision=None, window="sine"):
     key = (device if device is not None else _default["device"], precision or _default["precision"], int(sampleRate),
-           int(nMDCTLines), int(nScaleBits), int(nMantSizeBits), int(nTableIDBits), float(targetBitsPerSample))
+           int(nMDCTLines), int(nScaleBits), int(nMantSizeBits), int(nTableIDBits), float(targetBitsPerSample), window)
     e = _engines.get(key)
     if e is None:
-        e = Engine(key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7])
+        e = Engine(key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7], window=window)
         _engines[key] = e
     return e
 
@@ -589,4 +589,5 @@ def engine(sampleRate=44100, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4, nTa
 def engine_for(cp):
     """Engine matching a reference-style CodingParams attribute bag."""
     return engine(getattr(cp, "sampleRate", 44100), getattr(cp, "nMDCTLines", 1024), getattr(cp, "nScaleBits", 4),
-                  getattr(cp, "nMantSizeBits", 4), getattr(cp, "nTableIDBits", 4), getattr(cp, "targetBitsPerSample", 2.27))
+                  getattr(cp, "nMantSizeBits", 4), getattr(cp, "nTableIDBits", 4), getattr(cp, "targetBitsPerSample", 2.27),
+                  window=getattr(cp, "window", "sine"))

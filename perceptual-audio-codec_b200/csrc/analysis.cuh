@@ -545,21 +545,25 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         int osc0 = 0, osc1 = 0;
         auto sectionC = [&]() {
             // ------------------------------------------------ C. SineWindow (in place) + MDCT + overall scale
+            const bool inPlace = tb.winInPlace != 0;              // SineWindow multiplies the block itself (window.py:37); KBDWindow a copy (:64)
             if constexpr (!FAST) {
-                for (int e = tid; e < 2 * N; e += NT) {
-                    int ch = e / N, n = e - ch * N;
-                    xt[ch * XS + n] *= tb.sinw[n];
+                if (inPlace) {
+                    for (int e = tid; e < 2 * N; e += NT) {
+                        int ch = e / N, n = e - ch * N;
+                        xt[ch * XS + n] *= tb.sinw[n];
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             T mx[2] = {0, 0};
             {
                 for (int e = tid; e < 2 * H; e += NT) {            // fold to M/2 complex points per channel
                     int ch = e / H, n = e - ch * H;
-                    const T *x = xt + ch * XS;
+                    const T *xc = xt + ch * XS;
+                    auto x = [&](int i) -> T { return inPlace ? xc[i] : xc[i] * tb.sinw[i]; };
                     int m0 = 2 * n, m1 = M - 1 - 2 * n;
-                    T u0 = m0 < H ? -x[3 * H - 1 - m0] - x[3 * H + m0] : x[m0 - H] - x[2 * H - 1 - (m0 - H)];
-                    T u1 = m1 < H ? -x[3 * H - 1 - m1] - x[3 * H + m1] : x[m1 - H] - x[2 * H - 1 - (m1 - H)];
+                    T u0 = m0 < H ? -x(3 * H - 1 - m0) - x(3 * H + m0) : x(m0 - H) - x(2 * H - 1 - (m0 - H));
+                    T u1 = m1 < H ? -x(3 * H - 1 - m1) - x(3 * H + m1) : x(m1 - H) - x(2 * H - 1 - (m1 - H));
                     sm.W[ch][n] = cmul(mk2<T>(u0, u1), tb.mdct_pre[n]);
                 }
                 __syncthreads();
@@ -615,7 +619,8 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             const T2 x2 = sm.XF[ch][PI(m)];               // (x[2m], x[2m+1])
             if constexpr (FAST) {
                 const T2 s2 = reinterpret_cast<const T2 *>(tb.sinw)[m], h2 = reinterpret_cast<const T2 *>(tb.hann)[m];
-                sm.W[ch][PI(m)] = mk2<T>((x2.x * s2.x) * h2.x, (x2.y * s2.y) * h2.y);      // window.py:37 then psychoac.py:428
+                if (tb.winInPlace) sm.W[ch][PI(m)] = mk2<T>((x2.x * s2.x) * h2.x, (x2.y * s2.y) * h2.y);      // window.py:37 then psychoac.py:428
+                else sm.W[ch][PI(m)] = mk2<T>(x2.x * h2.x, x2.y * h2.y);                                     // KBDWindow left the block alone
             } else {
                 sm.W[ch][m] = x2;
             }

@@ -33,7 +33,7 @@ struct BandInfo {
 template <typename T>
 struct DevTables {
     using T2 = typename Vec2<T>::type;
-    const T *sinw;        // [N]   sin((n+.5)pi/N)                       window.py:35-37
+    const T *sinw;        // [N]   the MDCT window: sin((n+.5)pi/N) window.py:35-37, or the KBD window (window.py:56-78) with PAC_WINDOW_KBD
     const T *hann;        // [N]   .5(1-cos(2pi(n+.5)/N))                window.py:49-51
     const T2 *tw;         // [M]   exp(-2pi i m/M), M = N/2: twiddles of the M- and M/2-point FFTs
     const T2 *tw_split;   // [M+1] exp(-2pi i k/N): real-FFT split
@@ -47,6 +47,8 @@ struct DevTables {
     T2 hann_w;            // exp(i pi/N): frequency-domain Hann taps
     T cnorm;              // 8/3*4/N^2                                   psychoac.py:448
     T imdct_scale;
+    int winInPlace;       // 1: the window multiplies the block in place, so the psychoacoustic model sees windowed data (SineWindow,
+                          //    SURVEY App. A Q1); 0: it is applied to a copy (KBDWindow) and only the MDCT sees it
 };
 
 // Static geometry + scan weights of the fp32 fast threshold evaluation (analysis.cuh: masked_curve_fast; numpy model

@@ -215,6 +215,18 @@ static void h_band_layout(int nMDCTLines, int sampleRate, int32_t *nLines) {
     }
 }
 
+// window.py:56-78 with alpha = 4: Kaiser points over N/2 + 1 samples, cumulative power of the first N/2, mirrored
+static void kbd_window_host(int N, double *w) {
+    auto i0 = [](double x) { double s = 1, t = 1, q = x * x / 4; for (int k = 1; k < 500; k++) { t *= q / ((double)k * k); s += t; if (t < s * 1e-18) break; } return s; };
+    const double Nf = (double)N;
+    const int half = N / 2;
+    std::vector<double> kz(half + 1);
+    double den = 0, d0 = i0(M_PI * 4.0);
+    for (int t = 0; t <= half; t++) { double u = 4.0 * t / Nf - 1.0, a = 1.0 - u * u; if (a < 0) a = 0; kz[t] = i0(4.0 * M_PI * sqrt(a)) / d0; den += kz[t] * kz[t]; }
+    double c = 0;
+    for (int t = 0; t < half; t++) { c += kz[t] * kz[t]; w[t] = w[N - 1 - t] = sqrt(c / den); }
+}
+
 template <typename T>
 static int build_tables(PacCtx *ctx, int N, TableSet<T> &ts) {
     using T2 = typename Vec2<T>::type;
@@ -240,6 +252,12 @@ static int build_tables(PacCtx *ctx, int N, TableSet<T> &ts) {
         sinw[n] = (T)sin((n + 0.5) * M_PI / Nf);                                   // window.py:35-37
         hann[n] = (T)(0.5 * (1 - cos(2.0 * (n + 0.5) * M_PI / Nf)));               // window.py:49-51
     }
+    if (ctx->p.window == PAC_WINDOW_KBD && N == ctx->N) {                          // window.py:56-78, alpha = 4 (the codec's own block size only)
+        std::vector<double> kw(N);
+        kbd_window_host(N, kw.data());
+        for (int n = 0; n < N; n++) sinw[n] = (T)kw[n];
+    }
+    ts.dev.winInPlace = (ctx->p.window == PAC_WINDOW_KBD && N == ctx->N) ? 0 : 1;
     double mx = 0;
     std::vector<double> mldd(M);
     for (int i = 0; i < M; i++) {
@@ -505,6 +523,7 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
     // would write images that neither this library nor the reference can decode
     if (params->nTableIDBits != 4) FAIL(PAC_E_ARG, "nTableIDBits must be 4 (the .pac reader hard-codes it, pacfile.py:189)");
     if (params->sampleRate < 8000 || params->sampleRate > 192000) FAIL(PAC_E_ARG, "unsupported sample rate");
+    if (params->window != PAC_WINDOW_SINE && params->window != PAC_WINDOW_KBD) FAIL(PAC_E_ARG, "window must be PAC_WINDOW_SINE or PAC_WINDOW_KBD");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(PAC_E_NODEVICE, "no CUDA device: the engine has no CPU fallback");
     if (device < 0 || device >= ndev) FAIL(PAC_E_ARG, "device %d out of range (%d devices)", device, ndev);
@@ -1600,15 +1619,7 @@ static int get_window(PacCtx *ctx, int kind, int N, const double **dptr) {
         double Nf = (double)N;
         if (kind == 0) for (int n = 0; n < N; n++) w[n] = sin((n + 0.5) * M_PI / Nf);                        // window.py:35-37
         else if (kind == 1) for (int n = 0; n < N; n++) w[n] = 0.5 * (1 - cos(2.0 * (n + 0.5) * M_PI / Nf)); // window.py:49-51
-        else {                                                                                              // window.py:56-78, alpha = 4
-            auto i0 = [](double x) { double s = 1, t = 1, q = x * x / 4; for (int k = 1; k < 500; k++) { t *= q / ((double)k * k); s += t; if (t < s * 1e-18) break; } return s; };
-            int half = N / 2;
-            std::vector<double> kz(half + 1);
-            double den = 0, d0 = i0(M_PI * 4.0);
-            for (int t = 0; t <= half; t++) { double u = 4.0 * t / Nf - 1.0, a = 1.0 - u * u; if (a < 0) a = 0; kz[t] = i0(4.0 * M_PI * sqrt(a)) / d0; den += kz[t] * kz[t]; }
-            double c = 0;
-            for (int t = 0; t < half; t++) { c += kz[t] * kz[t]; w[t] = w[N - 1 - t] = sqrt(c / den); }
-        }
+        else kbd_window_host(N, w.data());                                                                  // window.py:56-78, alpha = 4
         void *d = nullptr;
         CK(cudaMalloc(&d, (size_t)N * 8));
         CK(cudaMemcpy(d, w.data(), (size_t)N * 8, cudaMemcpyHostToDevice));

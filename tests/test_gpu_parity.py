@@ -726,6 +726,32 @@ def test_batched_wav_ingest_and_egress(gold_dir, manifest, tmp_path):
     assert want == pbat.encode_files([str(whole)], precision="fp64")[0]
 
 
+def test_kbd_window_engine_option(pb, oracle, gold_dir):
+    """Engine(window="kbd") = PAC_WINDOW_KBD: KBDWindow (window.py:56-78) in place of SineWindow at codec.py:59-60,239-240.
+    fp64: .pac bytes and decoded WAV == the reference's own files for that variant (tests/golden/kbd_piano.*, pinned in
+    tests/test_oracle.py); fp32: byte count within 1 % and a clean decode."""
+    import json
+    import oracle as omod
+    import pacb200_batch as pbat
+    rate, pcm = pbat.read_wav(os.path.join(gold_dir, "kbd_piano.wav"))
+    meta = json.load(open(os.path.join(gold_dir, "kbd_piano.json")))
+    want = open(os.path.join(gold_dir, "kbd_piano.wak"), "rb").read()
+    e = pb.Engine(0, "fp64", sampleRate=rate, window="kbd")
+    got = e.encode_batch(pcm[None])[0]
+    assert got == want
+    assert tuple(int(v) for v in e.last_final_state[0]) == (meta["bitDeposit_end"], meta["extraBits_end"])
+    dec, sr, ns = e.decode_batch([want])[0]
+    assert pbat.wav_bytes(dec, sr, ns) == open(os.path.join(gold_dir, "kbd_piano.out.wav"), "rb").read()
+    e.close()
+    e32 = pb.Engine(0, "fp32", sampleRate=rate, window="kbd")
+    g32 = e32.encode_batch(pcm[None])[0]
+    assert abs(len(g32) - len(want)) <= 0.01 * len(want)
+    d32 = e32.decode_batch([g32])[0][0]
+    ref = oracle.decode_stream(g32, window=1)[0]
+    assert np.max(np.abs(d32.astype(np.int32) - ref.astype(np.int32))) <= 1       # fp32 synthesis: within 1 LSB of the oracle's decode
+    e32.close()
+
+
 def test_output_capacity_error(e64):
     pcm = synth_pcm(1, 20000)
     with pytest.raises(Exception) as ei:
