@@ -892,7 +892,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     CK(cudaStreamWaitEvent(sC, ctx->evStart, 0));
 
     // ---- tile geometry per group, and the global tile numbering (buffer parity and events run across groups)
-    struct Group { int s0, Sc, TB, nTiles, tile0; int64_t maxBlocks; };
+    struct Group { int s0, Sc, TB, nTiles, tile0; int64_t maxBlocks; std::vector<int> tstart; };
     std::vector<Group> groups(nGroups);
     int64_t nworkMax = 0;
     int totalTiles = 0;
@@ -910,7 +910,27 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         if (TB < 8) TB = 8;
         if (TB > G.maxBlocks) TB = (int)G.maxBlocks;
         if (trace) TB = (int)G.maxBlocks;                    // taps are copied out once per group
-        G.TB = TB; G.nTiles = (int)((G.maxBlocks + TB - 1) / TB); G.tile0 = totalTiles;
+        // Tile boundaries.  Uniform tiles of TB blocks, except that the call's FIRST tile and LAST tile are cut into 1/8, 1/8, 1/4, 1/2:
+        // the first kernel then waits for 1/128 instead of 1/16 of a group's PCM to arrive from the host, and the scan+pack of
+        // the last tile -- the only one not hidden under a following analysis -- is 1/8 as long.  (Results do not depend on the tiling:
+        // test_images_independent_of_batching_tiling_and_smem_history.)
+        G.TB = TB;
+        G.tstart.clear();
+        {
+            const bool uniform = trace || getenv("PAC_TILE_BLOCKS") != nullptr || TB < 64;
+            const int nFull = (int)((G.maxBlocks + TB - 1) / TB);
+            for (int t = 0; t < nFull; t++) {
+                const int b0 = t * TB;
+                const int b1 = (int)std::min<int64_t>((int64_t)b0 + TB, G.maxBlocks);
+                const bool head = !uniform && g == 0 && t == 0 && nFull > 1, tail = !uniform && g == nGroups - 1 && t == nFull - 1 && nFull > 1;
+                const int len = b1 - b0;
+                if (head && len >= 64) { G.tstart.push_back(b0); G.tstart.push_back(b0 + len / 8); G.tstart.push_back(b0 + len / 4); G.tstart.push_back(b0 + len / 2); }
+                else if (tail && len >= 64) { G.tstart.push_back(b0); G.tstart.push_back(b0 + len / 2); G.tstart.push_back(b0 + len / 2 + len / 4); G.tstart.push_back(b0 + len / 2 + len / 4 + len / 8); }
+                else G.tstart.push_back(b0);
+            }
+            G.tstart.push_back((int)G.maxBlocks);
+        }
+        G.nTiles = (int)G.tstart.size() - 1; G.tile0 = totalTiles;
         totalTiles += G.nTiles;
         if ((int64_t)G.Sc * TB > nworkMax) nworkMax = (int64_t)G.Sc * TB;
     }
@@ -961,8 +981,8 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         while ((int)evs.size() < G.nTiles) { cudaEvent_t ev; e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; evs.push_back(ev); }
         mark(sC, "h2d begin", g);
         for (int t = 0; t < G.nTiles; t++) {
-            const int64_t a0 = (int64_t)t * G.TB * M;
-            int64_t a1 = (t == G.nTiles - 1) ? stride : (int64_t)(t + 1) * G.TB * M;
+            const int64_t a0 = (int64_t)G.tstart[t] * M;
+            int64_t a1 = (t == G.nTiles - 1) ? stride : (int64_t)G.tstart[t + 1] * M;
             if (a1 > stride) a1 = stride;
             if (a1 > a0) {
                 e = cudaMemcpy2DAsync(buf.template as<char>() + a0 * 4, (size_t)stride * 4, reinterpret_cast<const char *>(pcm + (int64_t)G.s0 * stride * 2) + a0 * 4,
@@ -993,10 +1013,10 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             d_out = ((g & 1) ? ctx->w_out2 : ctx->w_out).template as<uint8_t>();
             if (g >= 2) CK(cudaStreamWaitEvent(sB, ctx->evD[g & 1], 0));                  // its previous contents have been copied out
         }
-        int t = 0;
-        for (int b0 = 0; b0 < G.maxBlocks; b0 += TB, t++) {
+        for (int t = 0; t < G.nTiles; t++) {
+            const int b0 = G.tstart[t];
             const int tile = G.tile0 + t;
-            const int nb = (G.maxBlocks - b0 < TB) ? (int)(G.maxBlocks - b0) : TB;
+            const int nb = G.tstart[t + 1] - b0;
             const int pbuf = NBUF == 2 ? (tile & 1) : 0;
             AnalysisArgs<T> aa{};
             aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.template as<int64_t>() + s0; aa.blocks = nullptr;
