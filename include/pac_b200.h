@@ -122,6 +122,9 @@ int pac_timing_get(PacCtx *ctx, double *ms /*[PAC_NKINDS]*/, int64_t *count /*[P
  * pac_encode_batch).  NULL on failure.  Not tied to a context; free with pac_pinned_free. */
 void *pac_pinned_alloc(size_t nbytes);
 void  pac_pinned_free(void *p);
+/* measured host -> device copy bandwidth (GB/s) of a host buffer on `device`: for callers that place pinned memory by measurement
+ * when the OS does not tell which NUMA node a GPU hangs off (bench.py's e2e leg) */
+int   pac_h2d_bandwidth(const void *host, size_t nbytes, int device, double *gbs);
 
 /* ------------------------------------------------------------------ whole streams (the hot path) */
 /* ceil(n/nMDCTLines)+1: pcmfile.py:66-82 + the flush block of pacfile.py:355-365 */

@@ -74,6 +74,7 @@ def lib():
     L.pac_pinned_alloc.restype = vp
     L.pac_pinned_free.argtypes = [vp]
     L.pac_pinned_free.restype = None
+    L.pac_h2d_bandwidth.argtypes = [vp, C.c_size_t, C.c_int, dp]
     L.pac_band_layout.argtypes = [vp, i32p, i32p]
     L.pac_launch_count.argtypes = [vp]
     L.pac_launch_count.restype = C.c_int64
@@ -222,6 +223,15 @@ def pinned_empty(shape, dtype=np.uint8):
     n = int(np.prod(shape)) * dt.itemsize
     blk = _PinnedBlock(n)
     return np.asarray(blk)[:n].view(dt).reshape(shape)          # the view keeps blk alive through its base chain
+
+
+def h2d_bandwidth(arr, device=0):
+    """measured host -> device copy bandwidth (GB/s) of a numpy array's memory (pac_h2d_bandwidth)"""
+    g = C.c_double(0.0)
+    rc = lib().pac_h2d_bandwidth(C.c_void_p(arr.ctypes.data), arr.nbytes, int(device), C.byref(g))
+    if rc:
+        raise PacError(rc, "pac_h2d_bandwidth failed")
+    return float(g.value)
 
 
 class Engine(object):

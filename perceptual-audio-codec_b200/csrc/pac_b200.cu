@@ -617,6 +617,29 @@ extern "C" void *pac_pinned_alloc(size_t nbytes) {
 }
 extern "C" void pac_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
+// host -> device copy bandwidth of a (pinned) host buffer on `device`, GB/s: lets a caller that cannot learn the GPU's NUMA node from
+// the OS pick the host memory placement by measurement (bench.py's e2e leg)
+extern "C" int pac_h2d_bandwidth(const void *host, size_t nbytes, int device, double *gbs) {
+    if (!host || !nbytes || !gbs) return PAC_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return PAC_E_CUDA; }
+    void *d = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = PAC_E_CUDA;
+    float ms = 0.f;
+    if (cudaMalloc(&d, nbytes) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess &&
+        cudaMemcpy(d, host, nbytes, cudaMemcpyHostToDevice) == cudaSuccess &&            // warm
+        cudaEventRecord(e0, 0) == cudaSuccess && cudaMemcpyAsync(d, host, nbytes, cudaMemcpyHostToDevice, 0) == cudaSuccess &&
+        cudaEventRecord(e1, 0) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f) {
+        *gbs = (double)nbytes / ((double)ms * 1e-3) / 1e9;
+        rc = PAC_OK;
+    }
+    if (rc != PAC_OK) cudaGetLastError();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (d) cudaFree(d);
+    return rc;
+}
+
 extern "C" int pac_band_layout(PacCtx *ctx, int32_t *nLines, int32_t *nBands) {
     if (!ctx || !nLines || !nBands) return PAC_E_ARG;
     for (int b = 0; b < ctx->bands.nBands; b++) nLines[b] = ctx->nLines[b];

@@ -467,6 +467,7 @@ def test_full_corpus_fp32_within_tolerance_of_oracle(e32, oracle):
     mism = {"ba": 0, "sf": 0, "tableID": 0}
     cnt = {"ba": 0, "sf": 0, "tableID": 0}
     bytes_gpu = bytes_ref = 0
+    nmant = nmant_bad = 0
     for i, n in enumerate(names):
         enc, otr, _ = oracle.encode_stream(pcms[i], trace=True)
         nb = len(otr["lrms"])
@@ -486,17 +487,22 @@ def test_full_corpus_fp32_within_tolerance_of_oracle(e32, oracle):
             es_all.append(es.ravel())
         for f in mism:
             mism[f] += int(np.sum(tr[f][i][:nb] != otr[f])); cnt[f] += otr[f].size
+        # mantissa codes (codec.py:276-277) of every line coded by either side
+        coded = (np.repeat(otr["ba"], NL44, axis=2) > 0) | (np.repeat(tr["ba"][i][:nb], NL44, axis=2) > 0)
+        nmant += int(np.sum(coded)); nmant_bad += int(np.sum((tr["mant"][i][:nb] != otr["mant"]) & coded))
     es_all = np.concatenate(es_all)
     print("fp32 vs oracle over %d files / %d blocks: worst line error %.3f x tol; SMR error median %.3f x tol, 99.9 %% quantile "
           "%.3f x tol, over tolerance %d of %d values (%.4f %%) in %d blocks (peak-picking flips, worst %.2f dB); "
-          "M/S decision mismatches %d, overall-scale mismatches %d; mismatch rates %s; coded bytes %d vs %d (%+.4f %%)"
+          "M/S decision mismatches %d, overall-scale mismatches %d; mismatch rates %s, mantissa codes %.4f %% (%d of %d coded lines); "
+          "coded bytes %d vs %d (%+.4f %%)"
           % (len(names), nblk, worst_l, float(np.median(es_all)), float(np.quantile(es_all, 0.999)), nsmr_bad, nsmr,
              100.0 * nsmr_bad / nsmr, nblk_bad, float(es_all.max()) * 1e-4, nlr, nosc,
-             {f: "%.4f %%" % (100.0 * mism[f] / cnt[f]) for f in mism}, bytes_gpu, bytes_ref, 100.0 * (bytes_gpu / bytes_ref - 1)))
+             {f: "%.4f %%" % (100.0 * mism[f] / cnt[f]) for f in mism}, 100.0 * nmant_bad / max(nmant, 1), nmant_bad, nmant,
+             bytes_gpu, bytes_ref, 100.0 * (bytes_gpu / bytes_ref - 1)))
     assert worst_l <= 1.0
     assert nsmr_bad <= 1e-3 * nsmr and nblk_bad <= 0.02 * nblk and float(np.quantile(es_all, 0.999)) <= 1.0
     assert nlr <= 0.001 * nblk and nosc <= 0.001 * nblk
-    assert all(mism[f] <= 0.01 * cnt[f] for f in mism)
+    assert all(mism[f] <= 0.01 * cnt[f] for f in mism) and nmant_bad <= 0.01 * nmant
     assert abs(bytes_gpu / bytes_ref - 1) < 0.002
 
 
