@@ -40,6 +40,7 @@ __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
 // 4 KB window of the image in shared memory with coalesced 16 B loads and every lane walks it redundantly from
 // there (uniform control flow); a new window is fetched only when the walk leaves the current one (~13 links).
 constexpr int kIdxWin = 4096, kIdxWarps = 4;
+constexpr int kIdxBoundExceeded = -100;          // internal status: the chain holds more blocks than IndexArgs.maxBlocks
 
 __global__ void __launch_bounds__(32 * kIdxWarps) k_index(const IndexArgs a) {
     __shared__ __align__(16) uint8_t win[kIdxWarps][kIdxWin];
@@ -83,10 +84,11 @@ __global__ void __launch_bounds__(32 * kIdxWarps) k_index(const IndexArgs a) {
         }
         nb++;
     }
-    // more chunks than the caller's bound allows (a chain of undersized chunks): malformed, not silently truncated
+    // more chunks than the caller's bound allows: never silently truncated.  The bound is either generous (from the image length: then
+    // the file is malformed) or a hint from the header's sample count (then the caller walks again, counting first)
     if (st == 0 && nb == a.maxBlocks && pos + 4 <= end) {
         const uint32_t n0 = rd(pos);
-        if (pos + 4 + (int64_t)n0 + 4 <= end) st = PAC_E_FORMAT;
+        if (pos + 4 + (int64_t)n0 + 4 <= end) st = kIdxBoundExceeded;
     }
     if (lane == 0) { a.nBlocks[s] = nb; a.status[s] = st; }
 }

@@ -1207,9 +1207,15 @@ static int launch_synth(PacCtx *ctx, SynthArgs<T> &a, int64_t grid) {
     FAIL(PAC_E_ARG, "unsupported nMDCTLines");
 }
 
+constexpr int kRetryCounting = -101;      // internal: the header's block count was too small, walk the chains first
+
 template <typename T>
 static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg, const int64_t *pacLen, int S, int16_t *pcm, int64_t stride,
-                          int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate) {
+                          int64_t *nSamplesOut, int64_t *hdrNumSamples, int32_t *hdrSampleRate, bool countFirst) {
+    // countFirst = false: the number of blocks of a stream is taken from its header's sample count (what this encoder and the
+    // reference write, pacfile.py:237-246) and only VERIFIED by the one walk that also fills the chunk index; a stream whose chain
+    // holds more blocks than its header promises makes the call return kRetryCounting, and the caller repeats it with
+    // countFirst = true (a first walk counts the blocks of every chain, as round 1 always did).
     const int M = ctx->M, hdrB = header_bytes(ctx);
     const bool pacDev = is_device_ptr(pac), pcmDev = is_device_ptr(pcm);
     const int64_t minBlock = 2 * (4 + (ctx->ec.fixedBits + 7) / 8);
@@ -1246,12 +1252,14 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
     ia.maxBlocks = (int)((maxLen - hdrB) / minBlock + 1);
     ia.chunkPos = nullptr; ia.chunkLen = nullptr;
     ia.nBlocks = ctx->w_misc2.as<int32_t>(); ia.status = ctx->w_misc3.as<int32_t>();
-    { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(S + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ia); }
-    ctx->launches++;
-    CK(cudaGetLastError());
+    if (countFirst) {
+        { KTimer kt(ctx, PAC_K_INDEX); k_index<<<(S + kIdxWarps - 1) / kIdxWarps, 32 * kIdxWarps, 0, ctx->stream>>>(ia); }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaMemcpyAsync(hdr.data(), ctx->w_hdr.p, hdr.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(nblk.data(), ia.nBlocks, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(stt.data(), ia.status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     auto rd32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
     auto rd16 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); };
@@ -1266,6 +1274,18 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
             if ((int)rd16(h + 26 + 2 * b) != ctx->nLines[b]) FAIL(PAC_E_FORMAT, "stream %d: band layout differs from this context's", s);
         if (hdrSampleRate) hdrSampleRate[s] = (int32_t)rd32(h + 4);
         if (hdrNumSamples) hdrNumSamples[s] = rd32(h + 10);
+        if (!countFirst) {
+            // blocks the header promises: n samples were coded as ceil(n/M) + 1 blocks, and the header holds n, or n + M when n is a
+            // multiple of M (the padding rule as written, pacfile.py:240-242)
+            const int64_t hn = rd32(h + 10);
+            int64_t hint = (hn % M == 0) ? hn / M : hn / M + 2;
+            const int64_t byLen = (len[s] - hdrB) / minBlock + 1;
+            if (hint > byLen) hint = byLen;
+            if (hint < 1) hint = 1;
+            if (hint * M > stride) return kRetryCounting;      // the real count may still fit: count first
+            nblk[s] = (int32_t)hint; stt[s] = 0;
+        }
+        if (stt[s] == kIdxBoundExceeded) FAIL(PAC_E_FORMAT, "stream %d: more chunks than its length allows", s);
         if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s);   // pacfile.py:184
         if ((int64_t)nblk[s] * M > stride) FAIL(PAC_E_OVERFLOW, "stream %d decodes to %lld samples > strideSamples", s, (long long)nblk[s] * M);
         if (nblk[s] > maxBlocks) maxBlocks = nblk[s];
@@ -1323,11 +1343,19 @@ static int decode_batch_t(PacCtx *ctx, const uint8_t *pac, const int64_t *pacBeg
         int runsPerStream = (maxBlocks + sa.run) / sa.run;
         int rc = launch_synth<T>(ctx, sa, (int64_t)Sc * runsPerStream);
         if (rc) return rc;
+        std::vector<int32_t> ib((size_t)Sc * 2);
         CK(cudaMemcpyAsync(stt.data(), ctx->w_misc6.p, (size_t)Sc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ib.data(), ig.nBlocks, (size_t)Sc * 8, cudaMemcpyDeviceToHost, ctx->stream));     // blocks found, walk status
         CK(cudaStreamSynchronize(ctx->stream));
         int64_t maxS = 0;
         for (int s = 0; s < Sc; s++) {
+            if (ib[Sc + s] == kIdxBoundExceeded) {
+                if (!countFirst) return kRetryCounting;
+                FAIL(PAC_E_FORMAT, "stream %d: more chunks than its length allows", s0 + s);
+            }
+            if (ib[Sc + s]) FAIL(PAC_E_FORMAT, "stream %d: Only read a partial block of coded PACFile data", s0 + s);   // pacfile.py:184
             if (stt[s]) FAIL(PAC_E_FORMAT, "stream %d: malformed chunk (bad table ID or code)", s0 + s);
+            nblk[s0 + s] = ib[s];
             nSamplesOut[s0 + s] = (int64_t)nblk[s0 + s] * M;
             if (nSamplesOut[s0 + s] > maxS) maxS = nSamplesOut[s0 + s];
         }
@@ -1342,8 +1370,14 @@ extern "C" int pac_decode_batch_strided(PacCtx *ctx, const uint8_t *pac, const i
     if (!ctx) return PAC_E_ARG;
     if (!pac || !pacBeg || !pacLen || !pcm || !nSamplesOut || S <= 0) FAIL(PAC_E_ARG, "bad arguments to pac_decode_batch");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->precision == PAC_PRECISION_FP64) return decode_batch_t<double>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
-    return decode_batch_t<float>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate);
+    for (int pass = 0; pass < 2; pass++) {
+        const bool countFirst = pass == 1;
+        const int rc = ctx->precision == PAC_PRECISION_FP64
+                           ? decode_batch_t<double>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate, countFirst)
+                           : decode_batch_t<float>(ctx, pac, pacBeg, pacLen, S, pcm, strideSamples, nSamplesOut, hdrNumSamples, hdrSampleRate, countFirst);
+        if (rc != kRetryCounting) return rc;
+    }
+    FAIL(PAC_E_FORMAT, "chunk chain could not be indexed");
 }
 
 extern "C" int pac_decode_batch(PacCtx *ctx, const uint8_t *pac, const int64_t *pacOff, int S, int16_t *pcm,

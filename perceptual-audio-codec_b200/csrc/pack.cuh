@@ -53,7 +53,7 @@ __device__ __forceinline__ void put_bits(unsigned *buf, unsigned pos, unsigned v
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kPackWarps * 32)
+__global__ void __launch_bounds__(kPackWarps * 32, 5)
 k_pack(const PackArgs<T> a) {
     __shared__ unsigned sbuf[kPackWarps][kChunkWords + 4];      // word 0: the '<L nBytes' prefix, payload from word 1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -100,10 +100,16 @@ k_pack(const PackArgs<T> a) {
         int PbandL = -1;                                                   // P(lo_b), filled in when the walk reaches the band
         __syncwarp();
         int carry = 0;                                                     // token bits of all lines before this step
+        // the next step's line and band index are requested one step ahead (two registers): a step's own work is too short to cover the
+        // round trip (ncu: 22 % of the kernel's stall samples sat on the first use of x[i])
+        T xn = x[lane];
+        int bn = a.band_of_line[lane];
+#pragma unroll 1
         for (int g = 0; g < nGroups; g++) {
             const int i0 = 32 * g, i = i0 + lane;
-            const int bd = a.band_of_line[i];
-            const T xv = x[i];
+            const int bd = bn;
+            const T xv = xn;
+            if (g + 1 < nGroups) { xn = x[i + 32]; bn = a.band_of_line[i + 32]; }
             const unsigned pb = __shfl_sync(0xffffffffu, pbL, bd);
             const int bab = (int)(pb & 0xff), sfb = (int)(pb >> 8);
             unsigned code = 0, code2 = 0;
