@@ -106,10 +106,10 @@ __global__ void k_gather_headers(const uint8_t *pac, const int64_t *pacBeg, int 
 // one and a prefetched third (its load latency hides behind the 32 bits in front of it); aligned, clamped loads.
 // Reading past the chunk returns repeated bytes; `used > nbits` flags it afterwards.
 struct BitReader {
-    const uint32_t *wp, *wlast;
+    const uint32_t *wp, *wlast, *wbase;
     uint32_t w0, w1, w2;
     int bp;                      // bit offset of the cursor inside w0
-    int used, nbits;
+    int off0, nbits;             // bit offset of the chunk's first bit inside *wbase; chunk size in bits
     __device__ __forceinline__ uint32_t word() {
         uint32_t v = __ldg(wp < wlast ? wp : wlast);
         wp++;
@@ -120,16 +120,19 @@ struct BitReader {
         wp = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);
         bp = (int)(A & 3) * 8 + (bitpos & 7);
         w0 = word(); w1 = word(); w2 = word();
-        used = bitpos;
     }
     __device__ __forceinline__ void init(const uint8_t *p, int nbytes) {
         nbits = nbytes * 8;
         wlast = reinterpret_cast<const uint32_t *>(((uintptr_t)p + (uintptr_t)(nbytes > 0 ? nbytes - 1 : 0)) & ~(uintptr_t)3);
+        wbase = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
+        off0 = (int)((uintptr_t)p & 3) * 8;
         seek(p, 0);
     }
+    // bits consumed since the start of the chunk, from the cursor itself (w0 is the word three behind wp): nothing to maintain per token
+    __device__ __forceinline__ int used() const { return ((int)(wp - wbase) - 3) * 32 + bp - off0; }
     __device__ __forceinline__ uint32_t peek(int n) { return __funnelshift_l(w1, w0, bp) >> (32 - n); }     // 1 <= n <= 32
     __device__ __forceinline__ void skip(int n) {                                                           // 0 <= n <= 32
-        bp += n; used += n;
+        bp += n;
         if (bp >= 32) { bp -= 32; w0 = w1; w1 = w2; w2 = word(); }
     }
     __device__ __forceinline__ uint32_t get(int n) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a
                 continue;
             }
             BitReader sr = r;                                         // nLines sign bits first (:202-204) ...
-            r.seek(p, r.used + (hi - lo));                            // ... then the codes
+            r.seek(p, r.used() + (hi - lo));                            // ... then the codes
             const uint32_t signBit = 1u << (ba - 1);
             uint32_t sbits = 0;                                       // up to 32 buffered sign bits, next one in bit 31
             int sleft = 0;
@@ -233,15 +236,18 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a
                     r.skip(kLutBits);
                     while (a.dt.sym[node] == -2) {
                         node = a.dt.child[2 * node + (int)r.get(1)];
-                        if (node < 0 || r.used > r.nbits) { bad = true; break; }
+                        if (node < 0 || r.used() > r.nbits) { bad = true; break; }
                     }
                     if (bad) break;
                     sym = a.dt.sym[node];
                 }
-                uint32_t m = sym < 0 ? r.get(ba) : (uint32_t)sym;     // escape: Huffman.py:326-327
+                uint32_t m = (uint32_t)sym;
+                if (sym < 0) {                                        // escape: the magnitude follows in ba raw bits (Huffman.py:326-327)
+                    m = r.get(ba);
+                    if (m >= signBit) { bad = true; break; }          // its top bit is always 0 (Huffman.py:296-298 writes ba bits of a
+                }                                                     // ba-1 bit magnitude); table symbols are < 2^15 by construction
                 if (sbits >> 31) m += signBit;                        // pacfile.py:210
                 sbits <<= 1; sleft--;
-                if (m > 0xffffu) { bad = true; break; }               // no ba <= 16 code is that large
                 if (a.o_mant) a.o_mant[c * M + i] = (int32_t)m;
                 if (sink.row) sink.push(m, i);
                 i++;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const UnpackArgs<T> a
         }
         uint32_t lr = 0;
         for (int bd = 0; bd < NB; bd++) lr |= r.get(1) << bd;         // :216-217
-        if (r.used > r.nbits) bad = true;
+        if (r.used() > r.nbits) bad = true;
         if ((c & 1) == 1) a.lrms[w] = lr;                             // the last channel's copy wins
         if (bad && a.err) a.err[s] = PAC_E_FORMAT;
     }

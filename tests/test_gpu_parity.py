@@ -765,6 +765,20 @@ def test_output_capacity_error(e64):
     assert "OVERFLOW" in str(ei.value)
 
 
+def test_decode_does_not_trust_the_header_for_the_block_count(e64, oracle):
+    """The decoder sizes its index from the header's sample count but only as a hint: the reference reads chunks until EOF whatever
+    the header says (pacfile.py:170-178), so a file whose header promises fewer (or more) samples than its chain holds must decode to
+    the same PCM as the oracle's -- through the counting fallback of pac_decode_batch."""
+    import struct
+    pcm = synth_pcm(41, 20 * 1024 + 77)
+    pac = oracle.encode_stream(pcm)[0]
+    for fake in (1024, 3 * 1024 + 5, 10 ** 6):
+        lied = pac[:10] + struct.pack("<L", fake) + pac[14:]
+        got, sr, hn = e64.decode_batch([lied, pac])[0]
+        want, _, whn = oracle.decode_stream(lied)
+        assert hn == fake == whn and np.array_equal(got, want), fake
+
+
 def test_malformed_pac_rejected(e64, oracle):
     pac = oracle.encode_stream(synth_pcm(1, 5000))[0]
     with pytest.raises(Exception) as ei:
