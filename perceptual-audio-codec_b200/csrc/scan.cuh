@@ -91,9 +91,10 @@ __device__ __forceinline__ int ba_count_ge(T smr, T tau, int lo, int cap) {
     int n = (int)g + 1;
     n = n < lo ? lo : n;
     n = n > cap ? cap : n;
-    while (n > lo && ba_key(smr, n - 1) < tau) n--;
-    while (n < cap && ba_key(smr, n) >= tau) n++;
-    return n;
+    // the guess is off by at most one (one rounding in the division): a single corrective step (tests/model_bitalloc.py asserts it)
+    const bool dec = n > lo && ba_key(smr, n - 1) < tau;
+    const bool inc = !dec && n < cap && ba_key(smr, n) >= tau;
+    return n - (dec ? 1 : 0) + (inc ? 1 : 0);
 }
 
 template <typename T>
@@ -105,9 +106,13 @@ __device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long ex
     const T NINF = (T)-INFINITY;
     int bits = 0;
     bool valid = inband;
-    long long total = total0;                                              // int(bitBudget + extraBits), :159
+    // int(bitBudget + extraBits), :159.  A whole channel costs at most 16 x 1024 bits, so any budget beyond +-2^30 behaves like 2^30:
+    // the loop runs on a clamped 32-bit budget and the difference is put back at the end
+    const long long clampLo = -(1ll << 30), clampHi = 1ll << 30;
+    const int total00 = (int)(total0 < clampLo ? clampLo : (total0 > clampHi ? clampHi : total0));
+    int total = total00;
     for (;;) {
-        valid = valid && (long long)nLinesLane <= total;                   // prune
+        valid = valid && nLinesLane <= total;                              // prune
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (!vmask) break;                                                 // :161
         const T kcur = ba_key(smrLane, bits);
@@ -136,16 +141,18 @@ __device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long ex
             cap = cap > maxMantBits ? maxMantBits : cap;
             int nb = ba_count_ge<T>(smrLane, flo, bits, cap);
             int cost = __reduce_add_sync(0xffffffffu, (nb - bits) * nLinesLane);
-            if ((long long)cost > total) {
+            if (cost > total) {
                 T hi = m + (T)1;                                           // nothing is >= hi
                 T lo = flo;
                 if (flo == NINF) lo = -wmax_on(-ba_key(smrLane, maxMantBits - 1), valid) - (T)1;
                 nb = bits; cost = 0;
-                for (int it = 0; it < 14; it++) {
+                // six probes: each further one would cost as much as the single iteration it saves (tests/model_bitalloc.py)
+#pragma unroll 1
+                for (int it = 0; it < 6; it++) {
                     const T mid = (lo + hi) * (T)0.5;
                     const int n2 = ba_count_ge<T>(smrLane, mid, bits, cap);
                     const int c2 = __reduce_add_sync(0xffffffffu, (n2 - bits) * nLinesLane);
-                    if ((long long)c2 <= total) { hi = mid; nb = n2; cost = c2; }
+                    if (c2 <= total) { hi = mid; nb = n2; cost = c2; }
                     else lo = mid;
                 }
             }
@@ -162,7 +169,7 @@ __device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long ex
         const T mxAll = F > mv ? F : mv;                                               // max over ALL bands (:165)
         const bool below = mxAll < (((lrms >> iMax) & 1u) ? (T)-5 : (T)-15);
         const int nl = __shfl_sync(0xffffffffu, nLinesLane, iMax);
-        const bool afford = total >= (long long)nl;                                    // :172
+        const bool afford = total >= nl;                                               // :172
         if (afford) total -= nl;
         if (lane == iMax) {
             if (below) valid = false;                                                  // still takes this iteration's bit
@@ -170,10 +177,10 @@ __device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long ex
             else valid = false;
         }
     }
-    unsigned ones = __ballot_sync(0xffffffffu, inband && bits == 1);       // bits == 1 -> 0 with refund (:179-180)
-    while (ones) { int bnd = __ffs(ones) - 1; ones &= ones - 1; total += __shfl_sync(0xffffffffu, nLinesLane, bnd); }
+    // bits == 1 -> 0 with refund (:179-180)
+    total += __reduce_add_sync(0xffffffffu, (inband && bits == 1) ? nLinesLane : 0);
     if (bits == 1) bits = 0;
-    *diff = total - extraBits;
+    *diff = (total0 - extraBits) + (long long)(total - total00);          // totalBits - extraBits (:182), the clamp put back
     return bits;
 }
 

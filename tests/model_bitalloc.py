@@ -74,14 +74,16 @@ def count_ge(smr_b, tau, lo, cap, T):
     g = np.floor((float(smr_b) - float(tau)) * (1.0 / 6.0))
     n = int(min(max(g, -1.0), 64.0)) + 1
     n = min(max(n, lo), cap)
-    while n > lo and key(smr_b, n - 1, T) < tau:
+    # the guess is off by at most one (one rounding in the division): a single corrective step, as the kernel does it branch-free
+    if n > lo and key(smr_b, n - 1, T) < tau:
         n -= 1
-    while n < cap and key(smr_b, n, T) >= tau:
+    elif n < cap and key(smr_b, n, T) >= tau:
         n += 1
+    assert (n == lo or key(smr_b, n - 1, T) >= tau) and (n == cap or key(smr_b, n, T) < tau), (smr_b, tau, lo, cap, n)
     return n
 
 
-def try_jump(bits, valid, total, smr, lrms, nl, maxb, T, probes=14):
+def try_jump(bits, valid, total, smr, lrms, nl, maxb, T, probes=6):
     """One event-free advance from the loop state (bits, valid, total).  Returns the new state and the number of bits handed out."""
     NB = len(nl)
     vb = [b for b in range(NB) if valid[b]]
