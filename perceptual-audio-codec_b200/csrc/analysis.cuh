@@ -528,7 +528,9 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                     int c = ch ? (v >> 16) : (int)(short)(v & 0xffff);
                     int code = c < 0 ? -c : c;
                     if (code & 32768) code -= 32768;          // -32768 dequantises to 0 (quantize.py:133-138)
-                    T f = (T)(2 * code) / (T)65535;           // quantize.py:141
+                    T f;                                      // quantize.py:141: 2 * code / 65535
+                    if constexpr (FAST) f = (float)(2 * code) * 1.5259021896696422e-05f;      // (psychoacoustic input only in fp32 mode: one rounding more, no division)
+                    else f = (T)(2 * code) / (T)65535;
                     xt[ch * XS + XI(n)] = c < 0 ? -f : f;
                 }
             }

@@ -799,14 +799,17 @@ static int launch_scan(PacCtx *ctx, ScanArgs<T> &a) {
         if (rc) return rc;
         a.band_of_line = tb.band_of_line;
     }
-    // one CTA per stream: warp 0 carries the serial state, all warps share the line phase (scan.cuh).  Many streams: the kernel is
-    // a throughput problem and runs beside k_analysis, where a CTA's register-time is what it costs -> 2 warps; few streams (a
-    // shard of the 8-GPU run): the per-stream chain is what matters -> 8 warps.  Results do not depend on the choice.
-    int warps = a.S >= 1536 ? 2 : (a.S >= 768 ? 4 : 8);
-    if (const char *we = getenv("PAC_SCAN_WARPS")) { const int v = atoi(we); if (v == 2 || v == 4 || v == 8) warps = v; }
+    // Warps per stream.  Many streams: the kernel is a throughput problem and runs beside k_analysis, where what a stream costs is its
+    // register-time -> ONE warp per stream (no partner warps idling at the barrier through the BitAllocs), four streams per CTA;
+    // fewer streams (the shards of a multi-GPU run): the per-stream chain matters more and more -> 2, 4, 8 warps, warp 0 carrying
+    // the serial state and all of them sharing the line phase (scan.cuh).  Results do not depend on the choice
+    // (test_images_independent_of_batching_tiling_and_smem_history runs every variant).
+    int warps = a.S >= 3072 ? 1 : (a.S >= 1024 ? 2 : (a.S >= 384 ? 4 : 8));      // measured: 4096 streams 1651 (1 warp) vs 1677 ms (2), 2048: 861 vs 854, 1024: 431 (2) vs 435 (4), 512: 223 (4) vs 225 (8)
+    if (const char *we = getenv("PAC_SCAN_WARPS")) { const int v = atoi(we); if (v == 1 || v == 2 || v == 4 || v == 8) warps = v; }
     {
         KTimer kt(ctx, PAC_K_SCAN);
-        if (warps == 2) k_scan<T, 2><<<a.S, 64, 0, LS(ctx)>>>(a);
+        if (warps == 1) k_scan<T, 1><<<(a.S + kScanSoloStreams - 1) / kScanSoloStreams, kScanSoloStreams * 32, 0, LS(ctx)>>>(a);
+        else if (warps == 2) k_scan<T, 2><<<a.S, 64, 0, LS(ctx)>>>(a);
         else if (warps == 4) k_scan<T, 4><<<a.S, 128, 0, LS(ctx)>>>(a);
         else k_scan<T, 8><<<a.S, 256, 0, LS(ctx)>>>(a);
     }

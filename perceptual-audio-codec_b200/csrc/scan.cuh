@@ -188,16 +188,29 @@ __device__ __forceinline__ int warp_bitalloc_jump(long long total0, long long ex
 // offset) and runs the two BitAllocs of a block; then ALL warps share the line phase (half of the warps per channel, each
 // a contiguous range of lines: quantise, look up the ten code lengths), whose loads were issued before the BitAllocs so
 // that their latency hides behind them; warp 0 finally picks the table and updates the state.  Two CTA barriers per block.
+// WARPS == 1 (many streams in flight: the kernel is a throughput problem and what a stream costs is its register-time): ONE warp
+// per stream does everything, both channels' line phases one after the other -- no partner warps idling at the barrier through the
+// BitAllocs (60 % of a block's latency); kScanSoloStreams such warps share a CTA and never synchronise with each other.
+constexpr int kScanSoloStreams = 4;
+#ifndef PAC_SCAN_SOLO_MINB
+#define PAC_SCAN_SOLO_MINB 8         // resident CTAs per SM the one-warp variant is compiled for (8 x 128 threads: 64 registers)
+#endif
 template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS == 1 ? kScanSoloStreams * 32 : WARPS * 32, WARPS == 1 ? PAC_SCAN_SOLO_MINB : 1)
 k_scan(const ScanArgs<T> a) {
-    static_assert(WARPS >= 2 && WARPS % 2 == 0, "half of the warps per channel");
-    constexpr int WPC = WARPS / 2;               // warps per channel
-    constexpr int LPLMAX = 1024 / (32 * WPC);    // lines per lane at M = 1024
-    __shared__ unsigned short sBitsSf[2][kMaxBands];      // bits | sf << 8 per (channel, band) of the current block
-    __shared__ unsigned sTot[WARPS][kNTables];            // per-warp totals of the ten table lengths
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = blockIdx.x;
+    static_assert(WARPS == 1 || (WARPS >= 2 && WARPS % 2 == 0), "half of the warps per channel");
+    constexpr bool SOLO = WARPS == 1;
+    constexpr int WPC = SOLO ? 1 : WARPS / 2;    // warps per channel
+    constexpr int LPLMAX = 1024 / (32 * WPC);    // lines per lane (and channel) at M = 1024
+    constexpr int SPC = SOLO ? kScanSoloStreams : 1;      // streams per CTA
+    __shared__ unsigned short sBitsSfAll[SPC][2][kMaxBands];       // bits | sf << 8 per (channel, band) of the current block
+    __shared__ unsigned sTotAll[SPC][SOLO ? 2 : WARPS][kNTables];  // per-warp (SOLO: per-channel) totals of the ten table lengths
+    const int lane = threadIdx.x & 31, warp = SOLO ? 0 : (int)(threadIdx.x >> 5);
+    const int slot = SOLO ? (int)(threadIdx.x >> 5) : 0;
+    auto &sBitsSf = sBitsSfAll[slot];
+    auto &sTot = sTotAll[slot];
+    auto sync = [&]() { if constexpr (SOLO) __syncwarp(); else __syncthreads(); };
+    const int s = SOLO ? (int)blockIdx.x * SPC + slot : (int)blockIdx.x;
     if (s >= a.S) return;
     const int NB = a.bands.nBands, M = a.M;
     const EncConsts &ec = a.ec;
@@ -238,10 +251,10 @@ k_scan(const ScanArgs<T> a) {
         // every warp: the first chunk of its lines of this block (they do not depend on the allocation), so that their
         // latency hides behind the BitAllocs; further chunks (fewer warps per stream) are fetched one chunk ahead below
         constexpr int CH = WARPS >= 8 ? (LPLMAX < 8 ? LPLMAX : 8) : 4;   // lines per lane per chunk (fewer in flight where registers count)
-        const T *xrow = a.lines + (w * 2 + myCh) * M + l0 + lane;
+        const T *xrow0 = a.lines + (w * 2 + myCh) * M + l0 + lane;
         T xv[CH];
 #pragma unroll
-        for (int j = 0; j < CH; j++) xv[j] = j < lpl ? xrow[j * 32] : (T)0;
+        for (int j = 0; j < CH; j++) xv[j] = j < lpl ? xrow0[j * 32] : (T)0;
         if (warp == 0) {
             const uint32_t lrms = lrmsN;
             const T smrL[2] = {smrN[0], smrN[1]}, bmaxL[2] = {bmaxN[0], bmaxN[1]};
@@ -267,16 +280,24 @@ k_scan(const ScanArgs<T> a) {
                 }
             }
         }
-        __syncthreads();
+        sync();
         // ---- line phase: code lengths under the 10 tables.  Per line one 32-byte LUT entry gives all ten lengths in 12-bit
         // packed slots (a lane's <= 32 lines cannot overflow a slot), escapes add bitAlloc raw bits (Huffman.py:292-298).
-        {
+#pragma unroll 1
+        for (int pass = 0; pass < (SOLO ? 2 : 1); pass++) {
+            const int chL = SOLO ? pass : myCh;                  // the channel whose lines this pass covers
+            const T *xrow = xrow0 + (SOLO ? pass * M : 0);
             unsigned long long acc0 = 0, acc1 = 0;
 #pragma unroll
             for (int c0 = 0; c0 < LPLMAX; c0 += CH) {
                 if (c0 >= lpl) break;
                 T xn[CH];
-                if (c0 + CH < LPLMAX) {
+                if constexpr (SOLO) {                            // next chunk of this channel, or (after channel 0's last) channel 1's first
+                    const bool more = c0 + CH < lpl;
+                    const T *nx = more ? xrow + (c0 + CH) * 32 : xrow + M;
+#pragma unroll
+                    for (int j = 0; j < CH; j++) xn[j] = (more ? c0 + CH + j < lpl : (pass == 0 && j < lpl)) ? nx[j * 32] : (T)0;
+                } else if (c0 + CH < LPLMAX) {
 #pragma unroll
                     for (int j = 0; j < CH; j++) xn[j] = c0 + CH + j < lpl ? xrow[(c0 + CH + j) * 32] : (T)0;
                 }
@@ -285,7 +306,7 @@ k_scan(const ScanArgs<T> a) {
                     const int j = c0 + jj;
                     if (j < lpl) {
                         const int bd = (bandsPacked[j >> 2] >> (8 * (j & 3))) & 0xff;
-                        const unsigned bs = sBitsSf[myCh][bd];
+                        const unsigned bs = sBitsSf[chL][bd];
                         const int bab = (int)(bs & 0xffu), sfb = (int)(bs >> 8);
                         if (bab > 0) {
                             unsigned mag = mant_mag(fabs((double)xv[jj]), sfb, largestScale, bab);
@@ -296,7 +317,7 @@ k_scan(const ScanArgs<T> a) {
                         }
                     }
                 }
-                if (c0 + CH < LPLMAX) {
+                if (c0 + CH < LPLMAX || SOLO) {
 #pragma unroll
                     for (int j = 0; j < CH; j++) xv[j] = xn[j];
                 }
@@ -305,10 +326,10 @@ k_scan(const ScanArgs<T> a) {
             for (int t = 0; t < 5; t++) {
                 const unsigned v0 = __reduce_add_sync(0xffffffffu, (unsigned)(acc0 >> (12 * t)) & 0xfffu);
                 const unsigned v1 = __reduce_add_sync(0xffffffffu, (unsigned)(acc1 >> (12 * t)) & 0xfffu);
-                if (lane == 0) { sTot[warp][t] = v0; sTot[warp][5 + t] = v1; }
+                if (lane == 0) { sTot[SOLO ? pass : warp][t] = v0; sTot[SOLO ? pass : warp][5 + t] = v1; }
             }
         }
-        __syncthreads();
+        sync();
         if (warp == 0) {
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {

@@ -626,6 +626,13 @@ def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
             os.environ["PAC_POISON_SMEM"] = pat
             assert eng.encode_batch(batch) == ref, pat
         os.environ.pop("PAC_POISON_SMEM", None)
+        # k_scan picks its warps per stream (1, 2, 4 or 8) from the number of streams in flight: every variant, same bytes
+        for warps in ("1", "2", "4", "8"):
+            os.environ["PAC_SCAN_WARPS"] = warps
+            os.environ["PAC_TILE_BLOCKS"] = "13"
+            assert eng.encode_batch(batch) == ref, ("scan warps", warps)
+            assert eng.encode_batch(batch[:7]) == ref[:7], ("scan warps", warps)        # 7 streams: a partly filled one-warp CTA
+        os.environ.pop("PAC_SCAN_WARPS", None)
         # host buffers are staged in double-buffered stream groups: the grouping must not show either
         for groups, tb in (("2", "8"), ("5", "13"), ("24", "100000")):
             os.environ["PAC_STAGE_GROUPS"] = groups
@@ -635,6 +642,7 @@ def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
         os.environ.pop("PAC_TILE_BLOCKS", None)
         os.environ.pop("PAC_POISON_SMEM", None)
         os.environ.pop("PAC_STAGE_GROUPS", None)
+        os.environ.pop("PAC_SCAN_WARPS", None)
 
 
 def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
