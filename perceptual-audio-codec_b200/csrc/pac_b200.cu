@@ -77,10 +77,11 @@ struct PacCtx {
     cudaStream_t ownStream = nullptr;
     cudaStream_t sA = nullptr, sB = nullptr;      // internal streams: analysis / scan+pack of consecutive tiles overlap
     cudaStream_t sC = nullptr;                    // copy stream: H2D of the next stream group / D2H of the previous one
+    cudaStream_t sM = nullptr;                    // fp32 mode: window+MDCT of the tiles ahead (k_mdct_enc), beside the analysis of the current one
     cudaEvent_t evH[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
     DBuf w_pcm2, w_out2;
     cudaEvent_t evStart = nullptr;
-    std::vector<cudaEvent_t> evA, evB, evG, evS[2];
+    std::vector<cudaEvent_t> evA, evB, evG, evS[2], evM;
     HBuf hostState;
     cudaStream_t launchStream = nullptr;          // stream the launch helpers currently target (default: ctx->stream)
     std::string err;
@@ -557,6 +558,7 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, lo));      // analysis: lowest priority
         CK(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, hi));      // scan + pack: highest
+        CK(cudaStreamCreateWithPriority(&ctx->sM, cudaStreamNonBlocking, lo));      // MDCT of the tiles ahead: lowest
         CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&ctx->sC, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->evH[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evD[i], cudaEventDisableTiming)); }
@@ -587,11 +589,13 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (ctx->sA) cudaStreamDestroy(ctx->sA);
     if (ctx->sB) cudaStreamDestroy(ctx->sB);
     if (ctx->sC) cudaStreamDestroy(ctx->sC);
+    if (ctx->sM) cudaStreamDestroy(ctx->sM);
     for (int i = 0; i < 2; i++) { if (ctx->evH[i]) cudaEventDestroy(ctx->evH[i]); if (ctx->evD[i]) cudaEventDestroy(ctx->evD[i]); }
     ctx->w_pcm2.release(); ctx->w_out2.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     for (cudaEvent_t e : ctx->evA) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->evB) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->evM) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->evG) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) for (cudaEvent_t e : ctx->evS[i]) cudaEventDestroy(e);
     ctx->hostState.release();
@@ -774,8 +778,8 @@ static int launch_mdct(PacCtx *ctx, const AnalysisArgs<float> &a) {
 static int launch_mdct(PacCtx *, const AnalysisArgs<double> &) { return PAC_OK; }     // fp64 mode: the MDCT is a section of k_analysis
 
 template <typename T>
-static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a) {
-    {   // fp32 mode: k_mdct first, on the same stream; k_analysis picks its lines and scales up from a.lines / a.oscale
+static int launch_analysis(PacCtx *ctx, AnalysisArgs<T> &a, bool withMdct = true) {
+    if (withMdct) {   // fp32 mode: k_mdct first, on the same stream; k_analysis picks its lines and scales up from a.lines / a.oscale
         int rcm = launch_mdct(ctx, a);
         if (rcm) return rcm;
     }
@@ -891,7 +895,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     }
     if (Sg > 8192) Sg = 8192;
     const int nGroups = (S + Sg - 1) / Sg;
-    cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC;
+    cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC, sM = ctx->sM;
 
     // ---- per-stream inputs and state for ALL streams, uploaded once
     CK(ctx->w_ns.ensure((size_t)S * 8));
@@ -916,6 +920,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     CK(cudaStreamWaitEvent(sA, ctx->evStart, 0));
     CK(cudaStreamWaitEvent(sB, ctx->evStart, 0));
     CK(cudaStreamWaitEvent(sC, ctx->evStart, 0));
+    CK(cudaStreamWaitEvent(sM, ctx->evStart, 0));
 
     // ---- tile geometry per group, and the global tile numbering (buffer parity and events run across groups)
     struct Group { int s0, Sc, TB, nTiles, tile0; int64_t maxBlocks; std::vector<int> tstart; };
@@ -960,7 +965,12 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         totalTiles += G.nTiles;
         if ((int64_t)G.Sc * TB > nworkMax) nworkMax = (int64_t)G.Sc * TB;
     }
-    const int NBUF = totalTiles > 1 ? 2 : 1;
+    // PAC_MDCT_AHEAD=1 (fp32 mode, experiment kept as an option): k_mdct_enc of tiles t+1, t+2 runs on its own stream BESIDE the analysis
+    // of tile t instead of in front of the analysis of its own tile (one more set of tile buffers).  Measured: 4096 x 60 s 1620.5 ->
+    // 1619.0 ms, 512 x 60 s 217.9 -> 214.3 ms -- the SMs are busy either way, a step costs the sum of its kernels' work; off by
+    // default because the per-kernel times of the overlapped MDCT then say nothing (bench.py's stage split reads them).
+    const bool ahead = sizeof(T) == 4 && !trace && getenv("PAC_MDCT_AHEAD") && atoi(getenv("PAC_MDCT_AHEAD")) != 0 && totalTiles > 2;
+    const int NBUF = totalTiles > 1 ? (ahead ? 3 : 2) : 1;
     const size_t szLines = (size_t)nworkMax * 2 * M * sizeof(T), szBand = (size_t)nworkMax * 2 * kMaxBands * sizeof(T);
     CK(ctx->w_lines.ensure(szLines * NBUF));
     CK(ctx->w_smr.ensure(szBand * NBUF));
@@ -979,6 +989,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     static const int evaTiming = getenv("PAC_EVA_TIMING") ? atoi(getenv("PAC_EVA_TIMING")) : 1;
     while ((int)ctx->evA.size() < totalTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, (evaTiming & 1) ? cudaEventDefault : cudaEventDisableTiming)); ctx->evA.push_back(e); }
     while ((int)ctx->evB.size() < totalTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, (evaTiming & 2) ? cudaEventDefault : cudaEventDisableTiming)); ctx->evB.push_back(e); }
+    while ((int)ctx->evM.size() < totalTiles) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evM.push_back(e); }
     while ((int)ctx->evG.size() < nGroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evG.push_back(e); }
     if (!pcmDev) { CK(ctx->w_pcm.ensure((size_t)Sg * stride * 4 + 16)); if (nGroups > 1) CK(ctx->w_pcm2.ensure((size_t)Sg * stride * 4 + 16)); }
     if (!outDev) { CK(ctx->w_out.ensure((size_t)Sg * cap)); if (nGroups > 1) CK(ctx->w_out2.ensure((size_t)Sg * cap)); }
@@ -1043,7 +1054,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             const int b0 = G.tstart[t];
             const int tile = G.tile0 + t;
             const int nb = G.tstart[t + 1] - b0;
-            const int pbuf = NBUF == 2 ? (tile & 1) : 0;
+            const int pbuf = tile % NBUF;
             AnalysisArgs<T> aa{};
             aa.pcm = d_pcm; aa.strideSamples = stride; aa.nSamples = ctx->w_ns.template as<int64_t>() + s0; aa.blocks = nullptr;
             aa.S = Sc; aa.b0 = b0; aa.nb = nb; aa.nwork = (int64_t)Sc * nb;
@@ -1053,11 +1064,20 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             aa.oscale = ctx->w_osc.template as<uint8_t>() + (size_t)nworkMax * 2 * pbuf;
             aa.lrms = ctx->w_lrms.template as<uint32_t>() + (size_t)nworkMax * pbuf;
             aa.dbg_mdct = nullptr; aa.dbg_bthr = nullptr;
-            if (tile >= 2) CK(cudaStreamWaitEvent(sA, ctx->evB[tile - 2], 0));            // tile buffer reuse
-            if (!pcmDev) CK(cudaStreamWaitEvent(sA, ctx->evS[g & 1][t], 0));              // this tile's samples have landed
+            cudaStream_t sFirst = ahead ? sM : sA;                                        // the stream of the tile's first kernel
+            if (tile >= NBUF) CK(cudaStreamWaitEvent(sFirst, ctx->evB[tile - NBUF], 0));   // tile buffer reuse
+            if (!pcmDev) CK(cudaStreamWaitEvent(sFirst, ctx->evS[g & 1][t], 0));          // this tile's samples have landed
+            int rc;
+            if (ahead) {
+                ctx->launchStream = sM;
+                rc = launch_mdct(ctx, aa);
+                if (rc) { ctx->launchStream = nullptr; return rc; }
+                CK(cudaEventRecord(ctx->evM[tile], sM));
+                CK(cudaStreamWaitEvent(sA, ctx->evM[tile], 0));
+            }
             if (t == 0) mark(sA, "analysis begin", g);
             ctx->launchStream = sA;
-            int rc = launch_analysis<T>(ctx, aa);
+            rc = launch_analysis<T>(ctx, aa, !ahead);
             if (rc) { ctx->launchStream = nullptr; return rc; }
             CK(cudaEventRecord(ctx->evA[tile], sA));
             if (t == G.nTiles - 1) mark(sA, "analysis end", g);
@@ -1164,7 +1184,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     }
     if (rc == PAC_OK) rc = collect_group(nGroups - 1);
     // fence: the caller's stream continues after everything issued here (also on the error path, so buffers can be reused)
-    cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC);
+    cudaStreamSynchronize(sM); cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC);
     if (timeline) {
         for (const Mark &m : marks) { float ms = 0; cudaEventElapsedTime(&ms, tl0, m.e); fprintf(stderr, "[pac timeline] group %d %-15s %9.2f ms\n", m.g, m.what, ms); cudaEventDestroy(m.e); }
         cudaEventDestroy(tl0);

@@ -633,6 +633,9 @@ def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
             assert eng.encode_batch(batch) == ref, ("scan warps", warps)
             assert eng.encode_batch(batch[:7]) == ref[:7], ("scan warps", warps)        # 7 streams: a partly filled one-warp CTA
         os.environ.pop("PAC_SCAN_WARPS", None)
+        os.environ["PAC_MDCT_AHEAD"] = "1"                      # optional three-stream schedule (fp32: MDCT of the tiles ahead on its own stream)
+        assert eng.encode_batch(batch) == ref, "mdct ahead"
+        os.environ.pop("PAC_MDCT_AHEAD", None)
         # host buffers are staged in double-buffered stream groups: the grouping must not show either
         for groups, tb in (("2", "8"), ("5", "13"), ("24", "100000")):
             os.environ["PAC_STAGE_GROUPS"] = groups
@@ -643,6 +646,7 @@ def test_images_independent_of_batching_tiling_and_smem_history(pb, prec):
         os.environ.pop("PAC_POISON_SMEM", None)
         os.environ.pop("PAC_STAGE_GROUPS", None)
         os.environ.pop("PAC_SCAN_WARPS", None)
+        os.environ.pop("PAC_MDCT_AHEAD", None)
 
 
 def test_fp32_mismatch_rate_reported(e32, oracle, gold_dir):
