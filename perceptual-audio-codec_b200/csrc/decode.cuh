@@ -285,8 +285,8 @@ template <typename T, int LOGM>
 struct SynthSmem {
     static constexpr int M = 1 << LOGM;
     using T2 = typename Vec2<T>::type;
-    // fp32, 1024 lines: the register-blocked radix-8 passes want one spare element per 8 in W (fft.cuh: pad8) and one spare float per 16
-    // in v (the last pass writes frequencies 8 apart per lane); the radix-4 path of the other instantiations ignores the padding
+    // (fp32, 1024 lines: the register-blocked radix-8 path addresses W and v through XOR swizzles, k_synth below; the spare elements
+    // of the rows are left over from the additive paddings it used before and keep the rows' alignment)
     static constexpr int WROW = M / 2 + M / 16 + 2;
     T2 W[2][WROW];               // folded spectrum / FFT workspace
     T v[2][M + M / 16];          // DCT-IV output
@@ -343,7 +343,13 @@ k_synth(const SynthArgs<T> a) {
     using T2 = typename Vec2<T>::type;
     constexpr int M = SS::M, N = 2 * M, NT = M / 4, H = M / 2;
     constexpr bool R8 = sizeof(T) == 4 && LOGM == 10;        // fp32, 1024 lines: register-blocked radix-8 FFT (see below)
-    auto VI = [](int i) { return R8 ? i + (i >> 4) : i; };   // position of v[i]
+    // Shared-memory layouts of the register-blocked path: XOR swizzles found by enumerating the access patterns (every load and store below
+    // then takes the minimum number of wavefronts).  v (floats): the last FFT pass writes v[2k], v[M-1-2k] for k = 8(t&7) + (t>>3) + 64p,
+    // the unfold reads ascending/descending runs; W (float2, half-warp per wavefront): linear n, t + 64r, 64g + j + 8r, 8t + r.
+    // (The additive paddings used before -- one spare per 16 / per 8 -- left the v stores 4-way and the linear W accesses 2-way
+    // conflicted: 39 % of the kernel's shared-memory wavefronts were replays.)
+    auto VI = [](int i) { return R8 ? i ^ ((i >> 2) & 31) : i; };   // position of v[i]
+    auto ZI = [](int i) { return i ^ ((i >> 3) & 15); };             // position of W[ch][i] (R8 only)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SS &sm = *reinterpret_cast<SS *>(smem_raw);
     const int tid = threadIdx.x;
@@ -416,8 +422,8 @@ k_synth(const SynthArgs<T> a) {
             if ((lrms >> bA) & 1u) { a0 = a0 - a1; a1 = a0 + a1; }
             if ((lrms >> bB) & 1u) { b0 = b0 - b1; b1 = b0 + b1; }
             const T2 pre = tb.mdct_pre[n];
-            sm.W[0][R8 ? pad8(n) : n] = cmul(mk2<T>(a0, b0), pre);
-            sm.W[1][R8 ? pad8(n) : n] = cmul(mk2<T>(a1, b1), pre);
+            sm.W[0][R8 ? ZI(n) : n] = cmul(mk2<T>(a0, b0), pre);
+            sm.W[1][R8 ? ZI(n) : n] = cmul(mk2<T>(a1, b1), pre);
         }
         __syncthreads();
         if constexpr (R8) {
@@ -429,13 +435,13 @@ k_synth(const SynthArgs<T> a) {
                 T2 *Z = sm.W[ch];
                 T2 x[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) x[r] = Z[pad8(t + (H / 8) * r)];
+                for (int r = 0; r < 8; r++) x[r] = Z[ZI(t + (H / 8) * r)];
                 dft8(x);
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
                     T2 y = x[brev3(p)];
                     if (p) y = cmul(y, tb.tw[2 * t * p]);                 // W_H^(t p), tw[m] = exp(-2 pi i m / M)
-                    Z[pad8(t + (H / 8) * p)] = y;
+                    Z[ZI(t + (H / 8) * p)] = y;
                 }
             }
             __syncthreads();
@@ -445,13 +451,13 @@ k_synth(const SynthArgs<T> a) {
                 T2 *Z = sm.W[ch];
                 T2 x[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) x[r] = Z[pad8(64 * g + j + 8 * r)];
+                for (int r = 0; r < 8; r++) x[r] = Z[ZI(64 * g + j + 8 * r)];
                 dft8(x);
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
                     T2 y = x[brev3(p)];
                     if (p) y = cmul(y, tb.tw[16 * j * p]);                // W_64^(j p)
-                    Z[pad8(64 * g + j + 8 * p)] = y;
+                    Z[ZI(64 * g + j + 8 * p)] = y;
                 }
             }
             __syncthreads();
@@ -460,7 +466,7 @@ k_synth(const SynthArgs<T> a) {
                 const T2 *Z = sm.W[ch];
                 T2 x[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) x[r] = Z[pad8(8 * t + r)];
+                for (int r = 0; r < 8; r++) x[r] = Z[ZI(8 * t + r)];
                 dft8(x);
                 const int kb = (t >> 3) + 8 * (t & 7);                    // frequency k = kb + 64 p
 #pragma unroll
