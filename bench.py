@@ -41,40 +41,7 @@ def log(*a):
 
 # ---------------------------------------------------------------- synthetic corpus
 
-def gen_streams(stream_ids, n, device):
-    """int16 [len(ids)][n][2] on `device`.  Stream s is seeded with 0x50414300 + s ('PAC\\0' + id): 3-8 sinusoids
-    (log-uniform 50 Hz..16 kHz, -30..-6 dBFS, independent L/R gains), Gaussian noise at -50..-25 dBFS (per-channel
-    fraction random), Poisson(2/s) transients = 5 ms exponentially decaying noise bursts at -12..-3 dBFS; clipped and
-    rounded to int16.  The bursts are rounded to integers BEFORE they are scattered in (integer atomics commute; float
-    atomics would make overlapping bursts depend on the order of arrival, i.e. the corpus would differ from run to run)."""
-    import torch
-    out = torch.empty(len(stream_ids), n, 2, dtype=torch.int16, device=device)
-    t = torch.arange(n, device=device, dtype=torch.float32) / FS
-    blen = int(0.005 * FS)
-    decay = torch.exp(-torch.arange(blen, device=device, dtype=torch.float32) / (blen / 4.0))
-    for j, s in enumerate(stream_ids):
-        g = torch.Generator(device=device)
-        g.manual_seed(0x50414300 + int(s))
-        u = lambda *shape: torch.rand(*shape, device=device, generator=g)
-        sig = torch.zeros(n, 2, device=device)
-        ntones = int(3 + torch.floor(u(1) * 6).item())
-        f = 50.0 * (320.0 ** u(ntones))
-        amp = 10 ** (-(6 + 24 * u(ntones, 2)) / 20)
-        ph = 6.2831853 * u(ntones)
-        for k in range(ntones):
-            sig += torch.sin(6.2831853 * f[k] * t + ph[k])[:, None] * amp[k][None, :]
-        sig += (10 ** (-(25 + 25 * u(1)) / 20)) * u(1, 2) * torch.randn(n, 2, device=device, generator=g)
-        nb = int(torch.poisson(torch.tensor([2.0 * n / FS], device=device), generator=g).item())
-        if nb > 0 and n > blen:
-            pos = (u(nb) * (n - blen)).long()
-            lvl = 10 ** (-(3 + 9 * u(nb)) / 20)
-        acc = (sig.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int32)
-        if nb > 0 and n > blen:
-            burst = torch.randn(nb, blen, 2, device=device, generator=g) * decay[None, :, None] * lvl[:, None, None]
-            idx = (pos[:, None] + torch.arange(blen, device=device)[None, :]).reshape(-1)
-            acc.index_add_(0, idx, (burst.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int32).reshape(-1, 2))
-        out[j] = acc.clamp(-32767, 32767).to(torch.int16)
-    return out
+from corpus import gen_streams, gen_streams_numpy  # noqa: E402  (integer Philox generator: identical samples under numpy, torch-CPU and torch-CUDA)
 
 
 # ---------------------------------------------------------------- clocks sampler (B200_PROFILING.md)
@@ -284,16 +251,14 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
     cores = os.cpu_count() or 1
-    # the corpus is defined by torch's CUDA generator (same seeds -> same streams as the repo arm).  Without a CUDA device the CPU
-    # generator draws DIFFERENT samples of the same signal model for the same seeds: say so in the line instead of staying silent.
-    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    corpus_note = "" if dev != "cpu" else " [no CUDA device: torch CPU generator, same signal model but not the same samples as the repo arm]"
+    # the corpus generator is integer arithmetic on a counter-based Philox (corpus.py): numpy here, torch on the GPU in the repo arm,
+    # bit-identical samples either way -- this arm needs neither torch nor a CUDA device
+    corpus_note = ""
     sec = args.ref_seconds
     n = int(sec * FS)
     S = cores
-    pcm = gen_streams(list(range(S)), n, dev).cpu().numpy()
+    pcm = gen_streams_numpy(list(range(S)), n)
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt = cpu_baseline_run(pcm, sec, cores)
@@ -333,7 +298,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity leg that rides on the cpu_baseline sample")
     ap.add_argument("--no-stages", action="store_true", help="skip the MDCT-only stage timing (roofline.stages)")
-    ap.add_argument("--decode", action="store_true", help="also time decode-only throughput of the coded corpus (extra 'decode' key)")
+    ap.add_argument("--decode", action="store_true", help="(default on; kept for old command lines) time decode-only throughput of the coded corpus")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode-only leg (extra 'decode' key with its own roofline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -439,7 +405,7 @@ def main():
 
     # ---- decode-only throughput (BASELINE.json configs[4]): the coded images are decoded where pac_encode_batch left them
     dec = None
-    if args.decode:
+    if not args.no_decode:
         Sd = min(len(mine), 1024)                         # bounded: the decoded PCM needs its own buffer next to the inputs
         ob_h = counts[mine].cpu().numpy()[:Sd]
         beg = np.arange(Sd, dtype=np.int64) * cap
@@ -608,7 +574,7 @@ def main():
         line = {"metric": "audio-seconds encoded per second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
-                "config": {"workload": "synthetic corpus %d x %.0f s 44.1 kHz stereo int16 (tones+noise+transients), %s mode, streams sharded s mod N"
+                "config": {"workload": "synthetic corpus %d x %.0f s 44.1 kHz stereo int16 (tones+noise+transients; corpus.py: counter-based Philox, integer arithmetic, bit-identical on CPU and GPU), %s mode, streams sharded s mod N"
                                        % (S, args.seconds, args.precision),
                            "streams": S, "seconds_per_stream": args.seconds, "blocks_per_stream": nblk, "targetBitsPerSample": args.tbps,
                            "cache": "inputs (%.1f GB per rank) far larger than the 126 MB L2; no flush needed" % (len(mine) * n * 4 / 1e9),

@@ -881,3 +881,13 @@ def test_codec_encode_tuple_structure(gold_dir, oracle):
     want = [oracle.sine_window(oracle.imdct(lines[ch], 1024, 1024)) for ch in range(2)]
     for got, w in ((dL, want[0]), (dR, want[1])):
         assert np.max(np.abs(got - w)) <= 1e-12 * max(np.max(np.abs(w)), 1e-300)
+
+
+@pytest.mark.gpu
+def test_corpus_generator_cuda_equals_numpy():
+    """The bench corpus generated on the GPU (torch CUDA backend of corpus.py) is the corpus the CPU arm generates with numpy."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import corpus
+    ids, n = [1, 2048, 4095], 3 * 44100 + 17
+    assert np.array_equal(corpus.gen_streams(ids, n, "cuda:0").cpu().numpy(), corpus.gen_streams_numpy(ids, n))

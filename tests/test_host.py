@@ -209,3 +209,27 @@ def test_hostile_pickle_in_cwd_is_refused(tmp_path, monkeypatch):
     monkeypatch.chdir(os.path.dirname(_pacb200.__file__))
     tabs = _pacb200.load_encoding_tables()               # the packaged fixture still loads
     assert sorted(tabs) == list(range(1, 11))
+
+
+def test_corpus_generator_is_backend_independent():
+    """bench.py's synthetic corpus (corpus.py): counter-based Philox4x32-10 (Random123 known answers) and integer-only per-sample
+    arithmetic, so the numpy and the torch backends give the same int16 samples -- the CPU arm of the bench encodes the very streams the
+    GPU arm does, wherever they were generated."""
+    import torch
+    sys.path.insert(0, REPO)
+    import corpus
+    z = np.zeros(1, dtype=np.int64)
+    assert [int(v[0]) for v in corpus.philox4x32(z, z, z, z, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.full(1, 0xffffffff, dtype=np.int64)
+    assert [int(v[0]) for v in corpus.philox4x32(f, f, f, f, 0xffffffff, 0xffffffff)] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    p = np.array([0x243f6a88], dtype=np.int64), np.array([0x85a308d3], dtype=np.int64), np.array([0x13198a2e], dtype=np.int64), np.array([0x03707344], dtype=np.int64)
+    assert [int(v[0]) for v in corpus.philox4x32(*p, 0xa4093822, 0x299f31d0)] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    ids, n = [0, 3, 77, 4095], 2 * 44100 + 123
+    a = corpus.gen_streams_numpy(ids, n)
+    b = corpus.gen_streams(ids, n, "cpu").numpy()
+    assert a.dtype == np.int16 and a.shape == (4, n, 2) and np.array_equal(a, b)
+    assert np.array_equal(corpus.gen_streams_numpy([77], n)[0], a[2])                       # a stream depends on its id only
+    x = a.astype(np.float64) / 32767.0
+    rms = 20 * np.log10(np.sqrt(np.mean(x ** 2, axis=1)))
+    assert np.all(rms < -3) and np.all(rms > -40) and np.abs(a).max() <= 32767
+    assert len({a[i].tobytes() for i in range(4)}) == 4
