@@ -66,6 +66,7 @@ struct FastSmem {
     unsigned short loudBase[M / 4 + 4];   // number of loud maskers below bin 4t ...
     unsigned char loudFlag[M / 4 + 4];    // ... and which of the bins 4t .. 4t+3 are loud (prefix at any bin = base + popc)
     float totD[16], totA[16];
+    float4 stash[2][M / 4];       // per thread: the static records (FastTables::lineRec) of its two lines in the warp's second half-chunk
 };
 // scratch layout inside the dead spectrum buffer
 template <int LOGM>
@@ -87,7 +88,9 @@ struct AnalysisSmem {
     static constexpr int ROW = FASTK ? M + M / 16 : M + 2;
     T2 XF[2][ROW];         // time samples x[ch][n] (viewed as T[2][2*ROW], padded in fp32 mode); later F1[ch][0..M]
     T2 W[2][ROW];          // FFT work; later F2_M, F2_S; finally the four per-line SMR candidate arrays
-    T Lb[2][M];            // scaled MDCT lines L, R
+    T Lb[FASTK ? 1 : 2][FASTK ? 4 : M];   // scaled MDCT lines L, R (fp64 / stage kernels).  fp32 mode keeps no buffer for them: they land in
+                                          // W by cp.async once the last curve has consumed its spectrum (8 KB less per CTA; a 196 KB carve-out
+                                          // with 60 KB of L1 instead of 27 measured no different: 1584.5 vs 1585.0 ms)
     T P[M + 8];            // |spectrum|^2 of the current curve
     static constexpr int MLM = FASTK ? 1 : M / 2;                // the direct evaluation's masker list (fp64 / mono kernels)
     T mz[MLM], mp[MLM], ml[MLM];         // Bark position, SPL, 0.367*max(SPL-40,0)
@@ -237,7 +240,8 @@ __device__ __forceinline__ double spl_any(double i) { return spl_of<double>(i); 
 
 template <int LOGM>
 __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, CurveScratch<LOGM> &cs, const float2 *F, int tap, float drop,
-                                                 const DevTables<float> *tbp, const FastTables *ftp, int lb0, int lb1, uint32_t kU0, uint32_t kU1) {
+                                                 const DevTables<float> *tbp, const FastTables *ftp, int lb0, int lb1, uint32_t kU0, uint32_t kU1,
+                                                 const float *linesSrc) {
     constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
     const DevTables<float> &tb = *tbp;
     const FastTables &ft = *ftp;
@@ -259,6 +263,13 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
     const float *w = ft.sD + tid, *wa = ft.sA + tid;
     const float wl0 = w[0], wl1 = w[NT], wl2 = w[2 * NT];
     __syncthreads();
+    // last curve only: its spectrum (W) is consumed, so the block's scaled L/R lines (k_mdct_enc's output, first read in section F)
+    // start travelling into W now, behind the rest of this curve
+    if (linesSrc) {
+        float *dst = reinterpret_cast<float *>(&sm.W[0][0]);
+        for (int e = tid; e < 2 * M / 4; e += NT) cp_async16_a(dst + 4 * e, linesSrc + 4 * e);
+        cp_async_commit_a();
+    }
     // 2. findpeaks on this thread's 4 bins (psychoac.py:158-191), masker intensities (:448), the ordered list of the loud maskers, and
     //    four scans over the bins through one shuffle ladder: loud count (int), plateau prefix (double), lower skirts (descending,
     //    all maskers), quiet upper skirts (ascending)
@@ -353,6 +364,10 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
         inc = fmaf(C, wa[5 * NT], hp);
         *reinterpret_cast<float4 *>(&cs.SA[k0]) = make_float4(fmaf(inc, wa[6 * NT], b0), fmaf(inc, wa[7 * NT], b1), fmaf(inc, wa[8 * NT], b2), fmaf(inc, wa[9 * NT], b3));
     }
+    // the static records of the first half-chunk's two lines are requested before the barrier: their latency hides behind it
+    // (consumed right after it, they cost 1 % of the step)
+    const float4 pre0 = ft.lineRec[lb0], pre1 = ft.lineRec[lb0 + 1];
+    const float4 prez = *reinterpret_cast<const float4 *>(&ft.lineZ[lb0]);
     __syncthreads();
     // 4. upper skirts of the loud maskers, pairwise, only over lines above them.  Warp w owns the 64-line half-chunks w
     //    and 2*NW-1-w, two adjacent lines per lane in each, so that every warp sees the same number of (masker, line)
@@ -370,14 +385,15 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
         // plateau as a range sum over the bins within half a Bark, threshold in quiet (psychoac.py:437,452-454)
         float x0, x1;
         {
-            const float4 r0 = ft.lineRec[l0], r1 = ft.lineRec[l0 + 1];
+            // second half-chunk: this thread's own copy in shared memory (staged once per CTA; the global loads, consumed at once, cost 1 %)
+            const float4 r0 = hh ? fs.stash[0][tid] : pre0, r1 = hh ? fs.stash[1][tid] : pre1;
             const unsigned w0 = __float_as_uint(r0.x), w1 = __float_as_uint(r1.x);
             const int pa0 = (int)(w0 & 0xffffu), pb0 = (int)(w0 >> 16), pa1 = (int)(w1 & 0xffffu), pb1 = (int)(w1 >> 16);
             const float pl0 = (float)(cs.Sp[pb0] - cs.Sp[pa0]), pl1 = (float)(cs.Sp[pb1] - cs.Sp[pa1]);
             x0 = fmaf(cs.SD[min(pb0, M - 1)], r0.y, fmaf(cs.SA[max(pa0 - 1, 0)], r0.z, pl0)) + r0.w;
             x1 = fmaf(cs.SD[min(pb1, M - 1)], r1.y, fmaf(cs.SA[max(pa1 - 1, 0)], r1.z, pl1)) + r1.w;
         }
-        const float4 zz = *reinterpret_cast<const float4 *>(&ft.lineZ[l0]);      // l0 is even: (z0_hi, z0_lo, z1_hi, z1_lo)
+        const float4 zz = hh ? *reinterpret_cast<const float4 *>(&ft.lineZ[l0]) : prez;      // l0 is even: (z0_hi, z0_lo, z1_hi, z1_lo)
         const float z0 = zz.x, z0l = zz.y;
         const float dz01 = (zz.z - zz.x) + (zz.w - zz.y);          // Bark gap to the lane's second line
         const uint32_t kU = hh ? kU1 : kU0;
@@ -499,6 +515,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
     }
     if (tid < 8) sm.P[M + tid] = 0;
     if constexpr (FAST && !MDCT_ONLY) { if (tid == 8) sm.fs.loud[M / 2] = make_float4(-INFINITY, 0.f, 0.f, __int_as_float(M)); }
+    if constexpr (FAST && !MDCT_ONLY) { sm.fs.stash[0][tid] = a.ft.lineRec[lineBase[1]]; sm.fs.stash[1][tid] = a.ft.lineRec[lineBase[1] + 1]; }
     for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
         // 32-bit division when the tile allows it (a 64-bit division is a ~100-instruction subroutine, paid by every CTA)
         const int s = a.nwork <= 0xffffffffll ? (int)((uint32_t)w / (uint32_t)a.nb) : (int)(w / a.nb);
@@ -509,6 +526,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             __syncthreads();
             if (tid < 8) sm.P[M + tid] = 0;
             if constexpr (FAST && !MDCT_ONLY) { if (tid == 8) sm.fs.loud[M / 2] = make_float4(-INFINITY, 0.f, 0.f, __int_as_float(M)); }
+            if constexpr (FAST && !MDCT_ONLY) { sm.fs.stash[0][tid] = a.ft.lineRec[lineBase[1]]; sm.fs.stash[1][tid] = a.ft.lineRec[lineBase[1] + 1]; }
             __syncthreads();
         }
         // ------------------------------------------------ A. load one 2048-sample stereo window
@@ -597,11 +615,8 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         };
         if constexpr (FAST) {
             // fp32 mode: window + MDCT + overall scale ran as their own fp64 kernel (mdct.cuh: k_mdct) and left the scaled L/R lines in
-            // a.lines and the scales in a.oscale.  The lines travel into Lb by cp.async while the spectra and the six curves are
-            // computed (section F is their first reader, and overwrites a.lines in place with the LRMS-selected lines).
-            const T *src = a.lines + w * 2 * M;
-            for (int e = tid; e < 2 * M / 4; e += NT) cp_async16_a(&sm.Lb[0][0] + 4 * e, src + 4 * e);
-            cp_async_commit_a();
+            // a.lines and the scales in a.oscale.  The lines travel into shared memory by cp.async during the last curve
+            // (masked_curve_fast; section F is their first reader, and overwrites a.lines in place with the LRMS-selected lines).
             osc0 = a.oscale[w * 2]; osc1 = a.oscale[w * 2 + 1];
         }
         if constexpr (MDCT_ONLY) sectionC();
@@ -711,7 +726,8 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 if (c == 2) { __syncthreads(); computeF2(); }      // W (scratch of the L/R curves, read until the end of their step 4) becomes F2
                 CurveScratch<LOGM> &cs = *reinterpret_cast<CurveScratch<LOGM> *>(c < 2 ? &sm.W[0][0] : &sm.XF[0][0]);
                 const float2 *src = c < 2 ? sm.XF[c] : sm.W[c & 1];
-                const float4 r = masked_curve_fast<LOGM>(sm, cs, src, c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, lineBase[0], lineBase[1], kU0, kU1);
+                const float4 r = masked_curve_fast<LOGM>(sm, cs, src, c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, lineBase[0], lineBase[1], kU0, kU1,
+                                                         c == 5 ? reinterpret_cast<const float *>(a.lines) + w * 2 * M : nullptr);
                 thr[c][0] = r.x; thr[c][1] = r.y; thr[c][2] = r.z; thr[c][3] = r.w;
             }
         } else {
@@ -723,9 +739,12 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             masked_curve<T, LOGM, S>(sm, tb, [&](int k) { return hann_tap<T>(sm.W[1], k, hw, hwc); }, (T)0, zl, zlo, tiq, a.tabd.zpeak, thr[5]);   // :562
         }
         // ------------------------------------------------ F. SMR candidates, band maxima, select
-        if constexpr (FAST) { cp_async_wait_a(); __syncthreads(); }       // the L/R lines have landed in Lb
+        if constexpr (FAST) { cp_async_wait_a(); __syncthreads(); }       // the L/R lines have landed (in W); the last curve's scratch (XF) is dead
         const uint32_t lrms = sm.lrms;
-        T *V = reinterpret_cast<T *>(&sm.W[0][0]);          // V[q][i], q = 0..3 (L,R,M,S), stride M
+        // V[q][i], q = 0..3 (L,R,M,S), stride M: fp64 in W; fp32 in XF, because W holds the lines there
+        T *V = reinterpret_cast<T *>(FAST ? &sm.XF[0][0] : &sm.W[0][0]);
+        T(*LB)[M] = nullptr;
+        if constexpr (FAST) LB = reinterpret_cast<T(*)[M]>(&sm.W[0][0]); else LB = sm.Lb;
         T outl[2][4];
         if constexpr (FAST) {
 #pragma unroll
@@ -734,7 +753,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int i = LI(j);
-            T xl = sm.Lb[0][i], xr = sm.Lb[1][i];
+            T xl = LB[0][i], xr = LB[1][i];
             T xm = (xl + xr) / 2, xs = (xl - xr) / 2;                                     // psychoac.py:551
             T sl = spl_any((T)4 * (xl * xl)) - (T)6.02 * (T)osc0;                        // :534
             T sr = spl_any((T)4 * (xr * xr)) - (T)6.02 * (T)osc1;                        // :535
@@ -761,8 +780,8 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 int i = LI(j);
-                a.dbg_mdct[(w * 2 + 0) * M + i] = sm.Lb[0][i];
-                a.dbg_mdct[(w * 2 + 1) * M + i] = sm.Lb[1][i];
+                a.dbg_mdct[(w * 2 + 0) * M + i] = LB[0][i];
+                a.dbg_mdct[(w * 2 + 1) * M + i] = LB[1][i];
             }
         }
         if (a.dbg_bthr) {
@@ -777,7 +796,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
             T v0 = -INFINITY, v1 = -INFINITY, m0 = 0, m1 = 0;
             const int lo = a.bands.lo[bd], hi = a.bands.lo[bd + 1];
             for (int i = lo + lane; i < hi; i += 32) {
-                T xl = sm.Lb[0][i], xr = sm.Lb[1][i];
+                T xl = LB[0][i], xr = LB[1][i];
                 T c0 = ms ? (xl + xr) / 2 : xl, c1 = ms ? (xl - xr) / 2 : xr;
                 v0 = fmax(v0, V[(ms ? 2 : 0) * M + i]);
                 v1 = fmax(v1, V[(ms ? 3 : 1) * M + i]);
