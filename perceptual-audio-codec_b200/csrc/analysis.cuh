@@ -240,14 +240,14 @@ __device__ __forceinline__ double spl_any(double i) { return spl_of<double>(i); 
 
 template <int LOGM>
 __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, true> &sm, CurveScratch<LOGM> &cs, const float2 *F, int tap, float drop,
-                                                 const DevTables<float> *tbp, const FastTables *ftp, int lb0, int lb1, uint32_t kU0, uint32_t kU1,
-                                                 const float *linesSrc) {
+                                                 const DevTables<float> *tbp, const FastTables *ftp, int hcA, int hcB, const float *linesSrc) {
     constexpr int M = 1 << LOGM, NT = M / 4, NW = NT / 32;
     const DevTables<float> &tb = *tbp;
     const FastTables &ft = *ftp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float K = 0.33219280948873623f;           // log2(10)/10
     auto &fs = sm.fs;
+    const int lb0 = 64 * hcA + 2 * lane, lb1 = 64 * hcB + 2 * lane;      // first of this lane's two lines in the warp's two half-chunks
     const int k0 = 4 * tid;
     // 1. power spectrum (optionally of the Hann-tapped spectrum)
     {
@@ -396,7 +396,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
         const float4 zz = hh ? *reinterpret_cast<const float4 *>(&ft.lineZ[l0]) : prez;      // l0 is even: (z0_hi, z0_lo, z1_hi, z1_lo)
         const float z0 = zz.x, z0l = zz.y;
         const float dz01 = (zz.z - zz.x) + (zz.w - zz.y);          // Bark gap to the lane's second line
-        const uint32_t kU = hh ? kU1 : kU0;
+        const uint32_t kU = ft.kUhc[hh ? hcB : hcA];      // bins whose upper skirt starts at or before the half-chunk's first / last line (static)
         // loud maskers below a bin k = base of its group of four + the loud ones among the group's bins below k
         auto loudBelow = [&](unsigned k) { return (int)fs.loudBase[k >> 2] + __popc((unsigned)fs.loudFlag[k >> 2] & ((1u << (k & 3u)) - 1u)); };
         const int mfull = loudBelow(kU & 0xffffu);            // upper skirt starts at or before the half-chunk
@@ -506,13 +506,6 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
         }
     }
 
-    // fp32: bins whose upper skirt starts at or before the first / last line of this warp's two half-chunks (static)
-    uint32_t kU0 = 0, kU1 = 0;
-    if constexpr (FAST) {
-        const int h0 = lineBase[0] & ~63, h1 = lineBase[1] & ~63;
-        kU0 = (uint32_t)a.ft.kcountU[h0] | (uint32_t)a.ft.kcountU[h0 + 63] << 16;
-        kU1 = (uint32_t)a.ft.kcountU[h1] | (uint32_t)a.ft.kcountU[h1 + 63] << 16;
-    }
     if (tid < 8) sm.P[M + tid] = 0;
     if constexpr (FAST && !MDCT_ONLY) { if (tid == 8) sm.fs.loud[M / 2] = make_float4(-INFINITY, 0.f, 0.f, __int_as_float(M)); }
     if constexpr (FAST && !MDCT_ONLY) { sm.fs.stash[0][tid] = a.ft.lineRec[lineBase[1]]; sm.fs.stash[1][tid] = a.ft.lineRec[lineBase[1] + 1]; }
@@ -726,7 +719,7 @@ k_analysis(const __grid_constant__ AnalysisArgs<T> a) {
                 if (c == 2) { __syncthreads(); computeF2(); }      // W (scratch of the L/R curves, read until the end of their step 4) becomes F2
                 CurveScratch<LOGM> &cs = *reinterpret_cast<CurveScratch<LOGM> *>(c < 2 ? &sm.W[0][0] : &sm.XF[0][0]);
                 const float2 *src = c < 2 ? sm.XF[c] : sm.W[c & 1];
-                const float4 r = masked_curve_fast<LOGM>(sm, cs, src, c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, lineBase[0], lineBase[1], kU0, kU1,
+                const float4 r = masked_curve_fast<LOGM>(sm, cs, src, c >= 4, c < 4 ? 15.f : 0.f, &a.tab, &a.ft, hcA, hcB,
                                                          c == 5 ? reinterpret_cast<const float *>(a.lines) + w * 2 * M : nullptr);
                 thr[c][0] = r.x; thr[c][1] = r.y; thr[c][2] = r.z; thr[c][3] = r.w;
             }

@@ -64,6 +64,8 @@ struct FastTables {
     const float *sD;             // [13][NT] descending scan weights: wl[3], ww[5], wc, wf[4]
     const float *sA;             // [10][NT] ascending scan weights: ww[5], wc, wf[4]
     float omD[16], omA[16];      // per-warp carry weights
+    uint32_t kUhc[32];           // per 64-line half-chunk h: kcountU[64h] | kcountU[64h + 63] << 16 (read from the constant bank where it is needed:
+                                 // as per-thread registers carried through the curves these were spilled and re-read from local memory)
 };
 
 // Encoder scalars derived from PacParams

@@ -380,6 +380,7 @@ static int build_fast_tables(PacCtx *ctx, int N, FastSet &fsd) {
     unsigned char *d = reinterpret_cast<unsigned char *>(fsd.mem);
     fsd.dev.lineRec = reinterpret_cast<const float4 *>(d + o_lr); fsd.dev.lineZ = reinterpret_cast<const float2 *>(d + o_lz);
     fsd.dev.binZ = reinterpret_cast<const float2 *>(d + o_bz); fsd.dev.kcountU = reinterpret_cast<const short *>(d + o_kc);
+    for (int h = 0; h < 32; h++) fsd.dev.kUhc[h] = 64 * h + 63 < M ? ((uint32_t)(unsigned short)kcountU[64 * h] | (uint32_t)(unsigned short)kcountU[64 * h + 63] << 16) : 0u;
     fsd.dev.binEU = reinterpret_cast<const uint2 *>(d + o_be);
     fsd.dev.sD = reinterpret_cast<const float *>(d + o_sD); fsd.dev.sA = reinterpret_cast<const float *>(d + o_sA);
     return PAC_OK;
