@@ -336,6 +336,7 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
     {
         int offs = incl - nl;
         double dbase = dincl - A3;
+        // (the three carry loops of this step were also tried unrolled with a guard instead of a warp-dependent trip count: 1520 -> 1538 ms)
         for (int i = 0; i < warp; i++) { offs += sm.wsum[i]; dbase += fs.wtot[i]; }
         cs.Sp[k0] = dbase; cs.Sp[k0 + 1] = dbase + A0; cs.Sp[k0 + 2] = dbase + A1; cs.Sp[k0 + 3] = dbase + A2;
         if (tid == NT - 1) cs.Sp[M] = dbase + A3;
@@ -437,17 +438,22 @@ __device__ __forceinline__ float4 masked_curve_fast(AnalysisSmem<float, LOGM, tr
                     x0 = ((x0 + t00) + t10) + t20 + t30;                   // ascending masker order, as the one-by-one loop
                     x1 = ((x1 + t01) + t11) + t21 + t31;
                 }
+                // maskers whose upper skirt starts INSIDE the half-chunk: per line a test against the skirt's first line.  Two per trip
+                // (the second slot reads the sentinel when the mask runs out: exponent -inf, first line M): their loads overlap
                 mk = mask & ~fullMask;
                 while (mk) {
-                    const int j = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const float4 p = fs.loud[base + j];
-                    const int eu = __float_as_int(p.w);
-                    const float e0 = fmaf(p.y, z0, p.x) + fmaf(p.y, z0l, p.z);
-                    const float e1 = fmaf(p.y, dz01, e0);
-                    const float t0 = ex2_approx(e0), t1 = ex2_approx(e1);
-                    x0 += (l0 >= eu) ? t0 : 0.f;
-                    x1 += (l0 + 1 >= eu) ? t1 : 0.f;
+                    const int ja = __ffs(mk) - 1; mk &= mk - 1;
+                    const int jb = __ffs(mk) - 1; mk &= mk - 1;
+                    const float4 pa = fs.loud[base + ja];
+                    const float4 pb = fs.loud[jb < 0 ? SENT : base + jb];
+                    const int eua = __float_as_int(pa.w), eub = __float_as_int(pb.w);
+                    const float ea0 = fmaf(pa.y, z0, pa.x) + fmaf(pa.y, z0l, pa.z), ea1 = fmaf(pa.y, dz01, ea0);
+                    const float eb0 = fmaf(pb.y, z0, pb.x) + fmaf(pb.y, z0l, pb.z), eb1 = fmaf(pb.y, dz01, eb0);
+                    const float ta0 = ex2_approx(ea0), ta1 = ex2_approx(ea1), tb0 = ex2_approx(eb0), tb1 = ex2_approx(eb1);
+                    x0 += (l0 >= eua) ? ta0 : 0.f;
+                    x1 += (l0 + 1 >= eua) ? ta1 : 0.f;
+                    x0 += (l0 >= eub) ? tb0 : 0.f;                         // ascending masker order, as before
+                    x1 += (l0 + 1 >= eub) ? tb1 : 0.f;
                 }
             }
         }
