@@ -2,6 +2,7 @@
 // workspace, tiling of (streams x blocks), H2D/D2H staging.  No CPU fallback anywhere: every entry point
 // either launches kernels or fails with an error code.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -855,6 +856,9 @@ template <typename T>
 static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const int64_t *nSamples, int S, uint8_t *out,
                           int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace) {
     const int M = ctx->M, NB = ctx->bands.nBands, hdrB = header_bytes(ctx);
+    const auto hostT0 = std::chrono::steady_clock::now();           // PAC_TIMELINE: host-side phases of the call
+    auto hostMs = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hostT0).count(); };
+    double hostMark[5] = {0, 0, 0, 0, 0}, setupMark[4] = {0, 0, 0, 0};
     const bool pcmDev = is_device_ptr(pcm);
     // out: device memory, or PINNED host memory (k_pack then writes every chunk straight into the caller's buffer while the next
     // tile is analysed: no staging image, no copy-back phase at the end of a group, and only the outBytes[s] bytes of an image ever
@@ -878,17 +882,29 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         // measured 76 k audio-s/s where the same streams device-resident ran at 101 k.  Two groups from 1024 streams on, so
         // that the first half's images travel back under the second half's kernels.
         size_t freeB = 0, totalB = 0;
-        int64_t stagingLimit = (int64_t)24 << 30;
-        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+        int64_t stagingLimit = (int64_t)64 << 30;
+        if (const char *sl = getenv("PAC_STAGE_LIMIT_GB")) { const int v = atoi(sl); if (v > 0) stagingLimit = (int64_t)v << 30; }   // experiments
+        // steady state (the staging buffers of an earlier call already hold the whole batch): no need to ask the driver
+        const bool heldFits = (pcmDev || ctx->w_pcm.cap >= (size_t)S * stride * 4 + 16) && (outDev || ctx->w_out.cap >= (size_t)S * cap);
+        if (heldFits) stagingLimit = std::max<int64_t>(stagingLimit, (int64_t)S * ((pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap)));
+        else if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
             const int64_t held = (int64_t)(ctx->w_pcm.cap + ctx->w_pcm2.cap + ctx->w_out.cap + ctx->w_out2.cap);   // reused, not extra
-            const int64_t avail = ((int64_t)freeB + held) / 2;
+            const int64_t avail = ((int64_t)freeB + held) / 2;       // the other half stays for the tile intermediates and the caller
             if (avail < stagingLimit) stagingLimit = avail;
         }
-        int64_t per = (pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap);
-        int64_t lim = stagingLimit / (2 * (per > 0 ? per : 1));
-        if (lim < 1) lim = 1;
-        int nG = (int)((S + lim - 1) / lim);
-        if (nG < 2 && S >= 1024) nG = 2;
+        const int64_t per = std::max<int64_t>((pcmDev ? 0 : stride * 4) + (outDev ? 0 : cap), 1);
+        int nG;
+        if ((int64_t)S * per <= stagingLimit && (outDev || S < 1024)) {
+            // The whole batch fits ONE staging buffer: a single group.  Nothing is double-buffered, the slab-wise H2D of the batch runs
+            // ahead of the kernels, and the kernels see all streams at once -- a group of 1024 streams runs at the 1024-stream rate
+            // (measured: 4 x 410 ms for 4096 x 60 s in four groups against 1520 ms for the same streams device-resident).
+            nG = 1;
+        } else {
+            int64_t lim = stagingLimit / (2 * per);
+            if (lim < 1) lim = 1;
+            nG = (int)((S + lim - 1) / lim);
+            if (nG < 2 && S >= 1024) nG = 2;      // pageable output: group g's images travel back under group g+1's kernels
+        }
         if (const char *ge = getenv("PAC_STAGE_GROUPS")) { const int f = atoi(ge); if (f > nG) nG = f < S ? f : S; }   // tests: force staging groups
         if (trace) nG = 1;
         Sg = (S + nG - 1) / nG;
@@ -896,6 +912,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     }
     if (Sg > 8192) Sg = 8192;
     const int nGroups = (S + Sg - 1) / Sg;
+    setupMark[0] = hostMs();
     cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC, sM = ctx->sM;
 
     // ---- per-stream inputs and state for ALL streams, uploaded once
@@ -917,6 +934,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         CK(cudaMemsetAsync(ctx->w_ovf.p, 0, (size_t)S * 4, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));               // the pageable vectors above go out of scope
     }
+    setupMark[1] = hostMs();
     CK(cudaEventRecord(ctx->evStart, ctx->stream));
     CK(cudaStreamWaitEvent(sA, ctx->evStart, 0));
     CK(cudaStreamWaitEvent(sB, ctx->evStart, 0));
@@ -972,6 +990,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     // default because the per-kernel times of the overlapped MDCT then say nothing (bench.py's stage split reads them).
     const bool ahead = sizeof(T) == 4 && !trace && getenv("PAC_MDCT_AHEAD") && atoi(getenv("PAC_MDCT_AHEAD")) != 0 && totalTiles > 2;
     const int NBUF = totalTiles > 1 ? (ahead ? 3 : 2) : 1;
+    setupMark[2] = hostMs();
     const size_t szLines = (size_t)nworkMax * 2 * M * sizeof(T), szBand = (size_t)nworkMax * 2 * kMaxBands * sizeof(T);
     CK(ctx->w_lines.ensure(szLines * NBUF));
     CK(ctx->w_smr.ensure(szBand * NBUF));
@@ -995,6 +1014,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     if (!pcmDev) { CK(ctx->w_pcm.ensure((size_t)Sg * stride * 4 + 16)); if (nGroups > 1) CK(ctx->w_pcm2.ensure((size_t)Sg * stride * 4 + 16)); }
     if (!outDev) { CK(ctx->w_out.ensure((size_t)Sg * cap)); if (nGroups > 1) CK(ctx->w_out2.ensure((size_t)Sg * cap)); }
 
+    setupMark[3] = hostMs();
     // PAC_TIMELINE=1: print when each group's copies and kernels ran (ms since the start of the call)
     struct Mark { cudaEvent_t e; const char *what; int g; };
     std::vector<Mark> marks;
@@ -1005,6 +1025,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
         cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({e, what, g});
     };
     if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, ctx->stream); }
+    hostMark[0] = hostMs();                                         // set-up done (state upload, buffers, events)
 
     // H2D of a group's PCM goes in time slabs (one per tile, all streams of the group: a strided 2-D copy), each with its own
     // event, so that the analysis of tile t starts as soon as samples < (t+1)*TB*M have landed -- the first kernel of the
@@ -1178,15 +1199,22 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     };
 
     if (!pcmDev) CK(h2d_group(0));
+    hostMark[1] = hostMs();                                         // first group's copies enqueued
     int rc = PAC_OK;
     for (int g = 0; g < nGroups && rc == PAC_OK; g++) {
         rc = enqueue_group(g);
+        if (g == 0) hostMark[2] = hostMs();                         // first group's kernels enqueued
         if (rc == PAC_OK && g >= 1) rc = collect_group(g - 1);
     }
     if (rc == PAC_OK) rc = collect_group(nGroups - 1);
+    hostMark[3] = hostMs();                                         // last group's byte counts are on the host
     // fence: the caller's stream continues after everything issued here (also on the error path, so buffers can be reused)
     cudaStreamSynchronize(sM); cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC);
+    hostMark[4] = hostMs();
     if (timeline) {
+        fprintf(stderr, "[pac timeline] host set-up: grouping %.2f ms, state upload %.2f, tile geometry %.2f, buffers+events %.2f\n", setupMark[0], setupMark[1], setupMark[2], setupMark[3]);
+        fprintf(stderr, "[pac timeline] host: set-up %.2f ms, first copies enqueued %.2f, first group's kernels enqueued %.2f, results collected %.2f, streams drained %.2f (%d group(s))\n",
+                hostMark[0], hostMark[1], hostMark[2], hostMark[3], hostMark[4], nGroups);
         for (const Mark &m : marks) { float ms = 0; cudaEventElapsedTime(&ms, tl0, m.e); fprintf(stderr, "[pac timeline] group %d %-15s %9.2f ms\n", m.g, m.what, ms); cudaEventDestroy(m.e); }
         cudaEventDestroy(tl0);
     }
