@@ -845,7 +845,8 @@ static int launch_pack(PacCtx *ctx, PackArgs<T> &a) {
 }
 
 // ------------------------------------------------------------------ encode (whole streams)
-// Schedule.  Streams are cut into groups (host buffers: as few as the staging budget allows, two from 1024 streams on; device buffers: one),
+// Schedule.  Streams are cut into groups (host buffers: ONE when the batch fits a single staging buffer, else as few as the staging budget
+// allows -- pageable output: two from 1024 streams on; device buffers: one),
 // a group into time tiles of TB blocks.  Three internal CUDA streams:
 //   sA (low priority)   k_analysis of every tile, in order
 //   sB (high priority)  k_scan + k_pack of every tile, in order, one tile behind sA (double-buffered intermediates)
@@ -876,11 +877,10 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     int Sg = S;
     const bool staged = !pcmDev || !outDev;
     if (staged) {
-        // Host buffers are staged group by group (double-buffered).  Groups are as LARGE as the staging budget allows: a
-        // group's serial reservoir chain (k_scan, ~50-70 us per block per stream whatever the group size) is only hidden
-        // while the group's own analysis lasts longer, i.e. from a few hundred streams up; eight groups of 256 streams
-        // measured 76 k audio-s/s where the same streams device-resident ran at 101 k.  Two groups from 1024 streams on, so
-        // that the first half's images travel back under the second half's kernels.
+        // Host buffers are staged group by group (double-buffered when there are several).  Groups are as LARGE as the staging budget
+        // allows: a group runs at the rate of its own stream count (the serial reservoir chain of k_scan is only hidden while the
+        // group's own analysis lasts longer; eight groups of 256 streams measured 76 k audio-s/s where the same streams device-resident
+        // ran at 101 k, four groups of 1024 streams 4 x 410 ms against 1520 ms for 4096 at once).
         size_t freeB = 0, totalB = 0;
         int64_t stagingLimit = (int64_t)64 << 30;
         if (const char *sl = getenv("PAC_STAGE_LIMIT_GB")) { const int v = atoi(sl); if (v > 0) stagingLimit = (int64_t)v << 30; }   // experiments
