@@ -989,7 +989,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     // 1619.0 ms, 512 x 60 s 217.9 -> 214.3 ms -- the SMs are busy either way, a step costs the sum of its kernels' work; off by
     // default because the per-kernel times of the overlapped MDCT then say nothing (bench.py's stage split reads them).
     const bool ahead = sizeof(T) == 4 && !trace && getenv("PAC_MDCT_AHEAD") && atoi(getenv("PAC_MDCT_AHEAD")) != 0 && totalTiles > 2;
-    const int NBUF = totalTiles > 1 ? (ahead ? 3 : 2) : 1;
+    const int NBUF = totalTiles > 1 ? (ahead ? 3 : 2) : 1;      // (a third set of tile buffers without the MDCT running ahead measured no gain: 512 x 60 s 204.8 vs 205.1 ms)
     setupMark[2] = hostMs();
     const size_t szLines = (size_t)nworkMax * 2 * M * sizeof(T), szBand = (size_t)nworkMax * 2 * kMaxBands * sizeof(T);
     CK(ctx->w_lines.ensure(szLines * NBUF));
