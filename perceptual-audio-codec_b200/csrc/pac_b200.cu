@@ -78,6 +78,7 @@ struct PacCtx {
     cudaStream_t ownStream = nullptr;
     cudaStream_t sA = nullptr, sB = nullptr;      // internal streams: analysis / scan+pack of consecutive tiles overlap
     cudaStream_t sC = nullptr;                    // copy stream: H2D of the next stream group / D2H of the previous one
+    cudaStream_t sD = nullptr;                    // k_drain: a tile's finished bytes -> the caller's pinned host image
     cudaStream_t sM = nullptr;                    // fp32 mode: window+MDCT of the tiles ahead (k_mdct_enc), beside the analysis of the current one
     cudaEvent_t evH[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
     DBuf w_pcm2, w_out2;
@@ -109,7 +110,7 @@ struct PacCtx {
     DecodeTables dt{};
     // workspaces
     DBuf w_pcm, w_out, w_ns, w_state, w_lines, w_smr, w_bmax, w_osc, w_lrms, w_ba, w_sf, w_tid, w_nby, w_coff,
-        w_trE, w_trD, w_hdr, w_ovf, w_dbg1, w_dbg2, w_misc, w_misc2, w_misc3, w_misc4, w_misc5, w_misc6;
+        w_trE, w_trD, w_hdr, w_ovf, w_dbg1, w_dbg2, w_misc, w_misc2, w_misc3, w_misc4, w_misc5, w_misc6, w_toff;
 };
 
 #define CK(call)                                                                                  \
@@ -561,6 +562,7 @@ static int ctx_init(PacCtx *ctx, int device, int precision, const PacParams *par
         CK(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, lo));      // analysis: lowest priority
         CK(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, hi));      // scan + pack: highest
         CK(cudaStreamCreateWithPriority(&ctx->sM, cudaStreamNonBlocking, lo));      // MDCT of the tiles ahead: lowest
+        CK(cudaStreamCreateWithPriority(&ctx->sD, cudaStreamNonBlocking, hi));      // drain: a handful of warps, placed promptly
         CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&ctx->sC, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->evH[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evD[i], cudaEventDisableTiming)); }
@@ -592,6 +594,7 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     if (ctx->sB) cudaStreamDestroy(ctx->sB);
     if (ctx->sC) cudaStreamDestroy(ctx->sC);
     if (ctx->sM) cudaStreamDestroy(ctx->sM);
+    if (ctx->sD) cudaStreamDestroy(ctx->sD);
     for (int i = 0; i < 2; i++) { if (ctx->evH[i]) cudaEventDestroy(ctx->evH[i]); if (ctx->evD[i]) cudaEventDestroy(ctx->evD[i]); }
     ctx->w_pcm2.release(); ctx->w_out2.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
@@ -611,7 +614,7 @@ extern "C" void pac_ctx_destroy(PacCtx *ctx) {
     DBuf *bufs[] = {&ctx->w_pcm, &ctx->w_out, &ctx->w_ns, &ctx->w_state, &ctx->w_lines, &ctx->w_smr, &ctx->w_bmax, &ctx->w_osc,
                     &ctx->w_lrms, &ctx->w_ba, &ctx->w_sf, &ctx->w_tid, &ctx->w_nby, &ctx->w_coff, &ctx->w_trE, &ctx->w_trD,
                     &ctx->w_hdr, &ctx->w_ovf, &ctx->w_dbg1, &ctx->w_dbg2, &ctx->w_misc, &ctx->w_misc2, &ctx->w_misc3,
-                    &ctx->w_misc4, &ctx->w_misc5, &ctx->w_misc6};
+                    &ctx->w_misc4, &ctx->w_misc5, &ctx->w_misc6, &ctx->w_toff};
     for (DBuf *b : bufs) b->release();
     delete ctx;
 }
@@ -913,7 +916,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     if (Sg > 8192) Sg = 8192;
     const int nGroups = (S + Sg - 1) / Sg;
     setupMark[0] = hostMs();
-    cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC, sM = ctx->sM;
+    cudaStream_t sA = ctx->sA, sB = ctx->sB, sC = ctx->sC, sM = ctx->sM, sD = ctx->sD;
 
     // ---- per-stream inputs and state for ALL streams, uploaded once
     CK(ctx->w_ns.ensure((size_t)S * 8));
@@ -940,6 +943,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     CK(cudaStreamWaitEvent(sB, ctx->evStart, 0));
     CK(cudaStreamWaitEvent(sC, ctx->evStart, 0));
     CK(cudaStreamWaitEvent(sM, ctx->evStart, 0));
+    CK(cudaStreamWaitEvent(sD, ctx->evStart, 0));
 
     // ---- tile geometry per group, and the global tile numbering (buffer parity and events run across groups)
     struct Group { int s0, Sc, TB, nTiles, tile0; int64_t maxBlocks; std::vector<int> tstart; };
@@ -991,6 +995,19 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     const bool ahead = sizeof(T) == 4 && !trace && getenv("PAC_MDCT_AHEAD") && atoi(getenv("PAC_MDCT_AHEAD")) != 0 && totalTiles > 2;
     const int NBUF = totalTiles > 1 ? (ahead ? 3 : 2) : 1;      // (a third set of tile buffers without the MDCT running ahead measured no gain: 512 x 60 s 204.8 vs 205.1 ms)
     setupMark[2] = hostMs();
+    // Pinned host output of a single-group batch: k_pack writes into a device image and k_drain (pack.cuh) moves every tile's finished
+    // byte ranges to the caller's image beside the next tile's analysis.  PAC_NO_DRAIN=1: k_pack writes across PCIe itself, as it does
+    // for multi-group batches.
+    const bool drain = outDev && !is_device_ptr(out) && nGroups == 1 && !trace && totalTiles > 1 && !getenv("PAC_NO_DRAIN");
+    uint8_t *drainImg = nullptr;
+    long long *drainOff = nullptr;
+    if (drain) {
+        CK(ctx->w_out.ensure((size_t)S * cap + 32));
+        CK(ctx->w_toff.ensure((size_t)totalTiles * S * 2 * sizeof(long long)));
+        const uintptr_t base = reinterpret_cast<uintptr_t>(ctx->w_out.p);
+        drainImg = ctx->w_out.template as<uint8_t>() + ((reinterpret_cast<uintptr_t>(outD) & 15) + 16 - (base & 15)) % 16;   // same alignment mod 16 as the host image
+        drainOff = ctx->w_toff.template as<long long>();
+    }
     const size_t szLines = (size_t)nworkMax * 2 * M * sizeof(T), szBand = (size_t)nworkMax * 2 * kMaxBands * sizeof(T);
     CK(ctx->w_lines.ensure(szLines * NBUF));
     CK(ctx->w_smr.ensure(szBand * NBUF));
@@ -1111,11 +1128,12 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             sa.ba = ctx->w_ba.template as<uint8_t>(); sa.sf = ctx->w_sf.template as<uint8_t>(); sa.tableID = ctx->w_tid.template as<uint8_t>();
             sa.nbytes = ctx->w_nby.template as<uint32_t>(); sa.chunkOff = ctx->w_coff.template as<long long>();
             sa.trExtra = trace ? ctx->w_trE.template as<long long>() : nullptr; sa.trDeposit = trace ? ctx->w_trD.template as<long long>() : nullptr;
+            if (drain) { sa.tileBeg = drainOff + (size_t)tile * S * 2; sa.tileEnd = sa.tileBeg + S; }
             if ((rc = launch_scan<T>(ctx, sa))) { ctx->launchStream = nullptr; return rc; }
             PackArgs<T> pa{};
             pa.S = Sc; pa.b0 = b0; pa.nb = nb; pa.nSamples = aa.nSamples;
             pa.lines = aa.lines; pa.ba = sa.ba; pa.sf = sa.sf; pa.tableID = sa.tableID; pa.oscale = aa.oscale; pa.lrms = aa.lrms;
-            pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = d_out; pa.cap = cap; pa.perChunk = 0;
+            pa.nbytes = sa.nbytes; pa.chunkOff = sa.chunkOff; pa.out = drain ? drainImg : d_out; pa.cap = cap; pa.perChunk = 0;
             pa.overflow = ctx->w_ovf.template as<int>() + s0; pa.o_mant = nullptr;
             if (trace && trace->mant) {
                 CK(ctx->w_misc.ensure((size_t)nwork * 2 * M * 4));
@@ -1127,6 +1145,17 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
             ctx->launchStream = nullptr;
             if (rc) return rc;
             CK(cudaEventRecord(ctx->evB[tile], sB));
+            if (drain) {
+                CK(cudaStreamWaitEvent(sD, ctx->evB[tile], 0));
+                DrainArgs da{};
+                da.img = drainImg; da.dst = d_out; da.cap = cap; da.tileBeg = sa.tileBeg; da.tileEnd = sa.tileEnd; da.S = Sc;
+                int dgrid = ctx->numSMs / 4;
+                if (dgrid > (Sc + kDrainWarps - 1) / kDrainWarps) dgrid = (Sc + kDrainWarps - 1) / kDrainWarps;
+                if (dgrid < 1) dgrid = 1;
+                k_drain<<<dgrid, kDrainWarps * 32, 0, sD>>>(da);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
             if (trace) {      // single tile (TB == maxBlocks): copy the taps of this stream group
                 CK(cudaStreamSynchronize(sB));
                 const int64_t B = maxBlocksAll;
@@ -1209,7 +1238,7 @@ static int encode_batch_t(PacCtx *ctx, const int16_t *pcm, int64_t stride, const
     if (rc == PAC_OK) rc = collect_group(nGroups - 1);
     hostMark[3] = hostMs();                                         // last group's byte counts are on the host
     // fence: the caller's stream continues after everything issued here (also on the error path, so buffers can be reused)
-    cudaStreamSynchronize(sM); cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC);
+    cudaStreamSynchronize(sM); cudaStreamSynchronize(sA); cudaStreamSynchronize(sB); cudaStreamSynchronize(sC); cudaStreamSynchronize(sD);
     hostMark[4] = hostMs();
     if (timeline) {
         fprintf(stderr, "[pac timeline] host set-up: grouping %.2f ms, state upload %.2f, tile geometry %.2f, buffers+events %.2f\n", setupMark[0], setupMark[1], setupMark[2], setupMark[3]);

@@ -210,4 +210,44 @@ k_pack(const PackArgs<T> a) {
     }
 }
 
+// ---------------------------------------------------------------- K5b: drain a tile's bytes to the caller's pinned host image
+// Host-buffer encode with a PINNED `out`: k_pack could write every chunk straight across PCIe (and does when the batch is staged in
+// several groups), but its bursts (6 GB of a step's output inside the ~13 % of the step it runs) then queue behind the link and hold
+// the SM resources of a 2000-warp kernel while they wait: pack 200 -> 251 ms, analysis 1244 -> 1283 ms per 4096 x 60 s.  Instead k_pack
+// writes into a device image and this kernel -- a few warps, one stream per warp at a time -- copies the byte range every stream gained
+// in the tile ([tileBeg, tileEnd), recorded by k_scan) to the same offsets of the host image, at the link's pace, beside the next
+// tile's analysis.  Device image and host image have the same alignment modulo 16, so the body moves as 16-byte words.
+struct DrainArgs {
+    const uint8_t *img;              // [S][cap] device image
+    uint8_t *dst;                    // [S][cap] device-visible alias of the pinned host image
+    long long cap;
+    const long long *tileBeg, *tileEnd;   // [S]
+    int S;
+};
+constexpr int kDrainWarps = 4;
+__global__ void __launch_bounds__(kDrainWarps * 32) k_drain(const DrainArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * kDrainWarps;
+    for (int s = blockIdx.x * kDrainWarps + (threadIdx.x >> 5); s < a.S; s += nw) {
+        long long b = a.tileBeg[s], e = a.tileEnd[s];
+        if (e > a.cap) e = a.cap;                                   // an overflowing stream is reported through outBytes; nothing past its row
+        if (e <= b) continue;
+        const uint8_t *src = a.img + (long long)s * a.cap;
+        uint8_t *d = a.dst + (long long)s * a.cap;
+        long long b16 = b + (long long)((16 - ((uintptr_t)(d + b) & 15)) & 15);
+        if (b16 > e) b16 = e;
+        for (long long i = b + lane; i < b16; i += 32) d[i] = src[i];
+        const long long e16 = b16 + ((e - b16) & ~15ll);
+        long long i = b16 + 16 * lane;
+        for (; i + 3 * 512 < e16; i += 4 * 512) {                   // four 16-byte words in flight per lane
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(src + i), v1 = *reinterpret_cast<const uint4 *>(src + i + 512);
+            const uint4 v2 = *reinterpret_cast<const uint4 *>(src + i + 1024), v3 = *reinterpret_cast<const uint4 *>(src + i + 1536);
+            *reinterpret_cast<uint4 *>(d + i) = v0; *reinterpret_cast<uint4 *>(d + i + 512) = v1;
+            *reinterpret_cast<uint4 *>(d + i + 1024) = v2; *reinterpret_cast<uint4 *>(d + i + 1536) = v3;
+        }
+        for (; i < e16; i += 512) *reinterpret_cast<uint4 *>(d + i) = *reinterpret_cast<const uint4 *>(src + i);
+        for (long long j = e16 + lane; j < e; j += 32) d[j] = src[j];
+    }
+}
+
 }  // namespace pac

@@ -30,6 +30,8 @@ struct ScanArgs {
     uint32_t *nbytes;              // [nwork][2] payload bytes
     long long *chunkOff;           // [nwork][2] offset of the chunk's length prefix in the stream image
     long long *trExtra, *trDeposit;// [nwork] optional traces of the state after each block
+    long long *tileBeg, *tileEnd;  // [S] optional: byte range [beg, end) of the stream's image this tile produces (k_drain); the tile
+                                   //     with block 0 starts at 0 (k_pack writes the file header with block 0)
     const unsigned long long *lenLut;   // [kLenLutSize] 10 x 5-bit code lengths per magnitude (0 = escape)
     const ulonglong4 *lenLut4;          // [kLenLutSize+1] per magnitude: code length (or escape-code length) of tables 0-4 / 5-9 in
                                         // 12-bit slots, then 1 in the slot of every table that escapes this magnitude
@@ -218,7 +220,10 @@ k_scan(const ScanArgs<T> a) {
     int nblkStream = a.b0 + a.nb;
     if (a.nSamples) nblkStream = (int)((a.nSamples[s] + M - 1) / M + 1);
     long long extraBits = 0, bitDeposit = 0, outOff = 0;
-    if (warp == 0) { extraBits = a.state[s].extraBits; bitDeposit = a.state[s].bitDeposit; outOff = a.state[s].outOffset; }
+    if (warp == 0) {
+        extraBits = a.state[s].extraBits; bitDeposit = a.state[s].bitDeposit; outOff = a.state[s].outOffset;
+        if (lane == 0 && a.tileBeg) a.tileBeg[s] = a.b0 == 0 ? 0ll : outOff;
+    }
     const int nLinesLane = lane < NB ? a.bands.lo[lane + 1] - a.bands.lo[lane] : 0;
     const int bEnd = min(a.b0 + a.nb, nblkStream);
     // line phase geometry: this warp owns lines [l0, l0 + LPW) of channel myCh; lane l owns l0 + 32*j + l
@@ -366,6 +371,7 @@ k_scan(const ScanArgs<T> a) {
         a.state[s].extraBits = extraBits;
         a.state[s].bitDeposit = bitDeposit;
         a.state[s].outOffset = outOff;
+        if (a.tileEnd) a.tileEnd[s] = outOff;
     }
 }
 

@@ -1,5 +1,7 @@
-"""Does a host->device DMA stream running beside the kernels slow the device-resident encode? (diagnostic)"""
-import os, sys, time
+"""Does a host->device DMA stream running BESIDE the kernels slow the device-resident encode? (diagnostic)
+The copies must be enqueued after the call has uploaded its per-stream state: a pageable H2D copy queued behind gigabytes of DMA on
+the same copy engine would wait for them (that, not interference, is what a first version of this probe measured: 792 -> 1563 ms)."""
+import os, sys, threading, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "perceptual-audio-codec_b200")); sys.path.insert(0, ROOT)
@@ -19,16 +21,21 @@ dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
 side = torch.cuda.Stream()
 def run(copies):
     torch.cuda.synchronize()
+    res = {}
+    def enc():
+        t0 = time.time()
+        eng.encode_batch(pcm, out=out, cap=cap)          # ctypes releases the GIL; returns when the call's streams have drained
+        res["dt"] = time.time() - t0
+    th = threading.Thread(target=enc)
+    th.start()
+    time.sleep(0.03)                                     # the call is past its set-up and its kernels are running
     if copies:
         with torch.cuda.stream(side):
             for _ in range(copies):
                 dst.copy_(src, non_blocking=True)
-    t0 = time.time()
-    eng.encode_batch(pcm, out=out, cap=cap)
-    torch.cuda.current_stream().synchronize()
-    dt = time.time() - t0
+    th.join()
     torch.cuda.synchronize()
-    return dt
+    return res["dt"]
 run(0)
-for copies in (0, 40, 0, 40):
+for copies in (0, 30, 0, 30):
     print("H2D copies beside the kernels: %2d GB -> encode %.1f ms" % (copies, run(copies) * 1e3))

@@ -709,6 +709,35 @@ def test_pinned_host_output_is_written_in_place(pb, oracle):
         img = out_p.numpy()[s]
         assert img[:ob[s]].tobytes() == want[s] == oracle.encode_stream(pcm[s, :ns[s]])[0], s
         assert np.all(img[ob[s]:] == 0xAB), s
+    # the same through several time tiles (k_pack -> device image -> k_drain moves every tile's byte ranges to the host image), with the
+    # host image at an odd address inside its pinned allocation, and with the drain switched off (k_pack writes across PCIe itself)
+    try:
+        os.environ["PAC_TILE_BLOCKS"] = "8"
+        for nodrain in (False, True):
+            if nodrain:
+                os.environ["PAC_NO_DRAIN"] = "1"
+            flat = torch.full((3 * cap + 64,), 0xCD, dtype=torch.uint8).pin_memory()
+            view = flat.numpy()[5:5 + 3 * cap].reshape(3, cap)
+            l0 = e.launches
+            _, ob2 = e.encode_batch(pcm_p.numpy(), nSamples=ns, out=view, cap=cap)
+            assert list(ob2) == list(ob)
+            for s in range(3):
+                assert view[s, :ob2[s]].tobytes() == want[s], (s, nodrain)
+                assert np.all(view[s, ob2[s]:] == 0xCD), (s, nodrain)
+            assert np.all(flat.numpy()[:5] == 0xCD) and np.all(flat.numpy()[5 + 3 * cap:] == 0xCD)
+            if not nodrain:
+                ndrain = e.launches - l0
+        os.environ.pop("PAC_NO_DRAIN", None)
+        l0 = e.launches
+        e.encode_batch(pcm_p.numpy(), nSamples=ns, out=out_p.numpy(), cap=cap)
+        assert e.launches - l0 == ndrain                        # (the drain kernels were launched: one more launch per tile than without)
+        os.environ["PAC_NO_DRAIN"] = "1"
+        l0 = e.launches
+        e.encode_batch(pcm_p.numpy(), nSamples=ns, out=out_p.numpy(), cap=cap)
+        assert e.launches - l0 < ndrain
+    finally:
+        os.environ.pop("PAC_TILE_BLOCKS", None)
+        os.environ.pop("PAC_NO_DRAIN", None)
     e.close()
 
 
