@@ -141,6 +141,10 @@ int64_t pac_encode_bound(PacCtx *ctx, int64_t nSamples);
  * pcm: interleaved int16 [S][strideSamples][2], host or device.  nSamples[s] <= strideSamples (host).
  * out: [S][cap] bytes, host or device; outBytes[s] (host) = bytes of stream s's complete .pac file image.  Only
  *      out[s][0 .. outBytes[s]) is defined afterwards: the rest of a row is left as it was.
+ * Host buffers: a pcm batch that fits one device staging buffer (up to 64 GB or half of the free device memory) is copied in slab by
+ *      slab ahead of the kernels, larger ones in double-buffered stream groups.  A PINNED (page-locked, device-mapped:
+ *      pac_pinned_alloc) out is filled while the kernels run -- only outBytes[s] bytes of an image cross PCIe, there is no copy-back
+ *      phase; a pageable out is staged on the device and copied back group by group.
  * finalState (host, may be NULL): [S][2] = (huffman.bitDeposit, cp.extraBits) at end of stream. */
 int pac_encode_batch(PacCtx *ctx, const int16_t *pcm, int64_t strideSamples, const int64_t *nSamples, int S,
                      uint8_t *out, int64_t cap, int64_t *outBytes, int64_t *finalState, const PacTrace *trace);
