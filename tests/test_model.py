@@ -214,3 +214,52 @@ def test_event_driven_bitalloc_equals_plain_loop():
         it_plain += i1; it_fast += i2
     print("single iterations per problem: plain %.1f, event-driven %.1f" % (it_plain / 1200.0, it_fast / 1200.0))
     assert it_fast * 5 < it_plain
+
+
+def test_synth_shared_memory_swizzles_are_conflict_free():
+    """k_synth's register-blocked IMDCT (decode.cuh) addresses its float2 workspace through ZI(i) = i ^ ((i >> 3) & 15) and its float
+    DCT-IV output through VI(i) = i ^ ((i >> 2) & 31).  Enumerate every access pattern of the kernel's 1024-line path and count
+    shared-memory wavefronts (32 four-byte banks; an 8-byte access is served per half-warp): each load and store must take the minimum.
+    The additive paddings used before (one spare element per 8 / per 16) took 1.5x and 2.7x as many."""
+    M, H = 1024, 512
+    ZI = lambda i: i ^ ((i >> 3) & 15)
+    VI = lambda i: i ^ ((i >> 2) & 31)
+
+    def wf(addrs, banks):
+        per = {}
+        for a in set(addrs):
+            per.setdefault(a % banks, set()).add(a)
+        return max(len(v) for v in per.values())
+
+    assert len({ZI(i) for i in range(H)}) == H and max(ZI(i) for i in range(H)) < H          # permutations of the rows: no padding needed
+    assert len({VI(i) for i in range(M)}) == M and max(VI(i) for i in range(M)) < M
+
+    def cost_z(Z):
+        c = 0
+        for hw in range(16):                                          # pre-twiddle stores: n = tid, tid + 256
+            for k in range(2):
+                c += wf([Z(16 * hw + l + 256 * k) for l in range(16)], 16)
+        for hw in range(4):                                           # 64 threads per channel
+            for r in range(8):
+                t = [16 * hw + l for l in range(16)]
+                c += wf([Z(x + 64 * r) for x in t], 16)                               # pass 1: t + 64 r (loads and stores)
+                c += wf([Z(64 * (x >> 3) + (x & 7) + 8 * r) for x in t], 16)         # pass 2: 64 g + j + 8 r
+                c += wf([Z(8 * x + r) for x in t], 16)                                # pass 3: 8 t + r
+        return c
+
+    def cost_v(V):
+        c = 0
+        for h in range(2):                                            # last pass: v[2k], v[M-1-2k], k = 8 (t & 7) + (t >> 3) + 64 p
+            for p in range(8):
+                ks = [((32 * h + l) >> 3) + 8 * ((32 * h + l) & 7) + 64 * p for l in range(32)]
+                c += wf([V(2 * k) for k in ks], 32) + wf([V(M - 1 - 2 * k) for k in ks], 32)
+        for warp in range(8):                                         # unfold: ascending / descending runs
+            for j in range(4):
+                i = [warp * 32 + l + 256 * j for l in range(32)]
+                c += wf([V(x + H if x < H else 3 * H - 1 - x) for x in i], 32)
+                c += wf([V(H - 1 - x if x < H else x - H) for x in i], 32)
+        return c
+
+    assert cost_z(ZI) == 32 + 3 * 32                                 # one wavefront per half-warp access
+    assert cost_v(VI) == 32 + 64                                     # one wavefront per warp access
+    assert cost_z(lambda i: i + (i >> 3)) == 192 and cost_v(lambda i: i + (i >> 4)) == 256   # what the paddings cost
