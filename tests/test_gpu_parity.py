@@ -804,6 +804,25 @@ def test_output_capacity_error(e64):
     with pytest.raises(Exception) as ei:
         e64.encode_batch(pcm[None], cap=2000)
     assert "OVERFLOW" in str(ei.value)
+    # the same through pinned host buffers and several tiles (device image + k_drain): the stream that does not fit is reported, its
+    # neighbour is complete, and nothing is written outside the rows
+    import torch
+    n = 40 * 1024
+    two = np.stack([synth_pcm(2, n), synth_pcm(3, n, "silence")])
+    want = e64.encode_batch(two)
+    cap = len(want[0]) - 100                                     # too small for stream 0, enough for the silent stream 1
+    assert cap > len(want[1])
+    flat = torch.full((2 * cap + 64,), 0xEE, dtype=torch.uint8).pin_memory()
+    view = flat.numpy()[32:32 + 2 * cap].reshape(2, cap)
+    try:
+        os.environ["PAC_TILE_BLOCKS"] = "8"
+        with pytest.raises(Exception) as ei:
+            e64.encode_batch(torch.from_numpy(two).pin_memory().numpy(), out=view, cap=cap)
+        assert "OVERFLOW" in str(ei.value)
+    finally:
+        os.environ.pop("PAC_TILE_BLOCKS", None)
+    assert view[1, :len(want[1])].tobytes() == want[1]
+    assert np.all(flat.numpy()[:32] == 0xEE) and np.all(flat.numpy()[32 + 2 * cap:] == 0xEE)
 
 
 def test_decode_does_not_trust_the_header_for_the_block_count(e64, oracle):
